@@ -1,0 +1,196 @@
+"""Seeded synthetic Gaussian clouds and cameras for the BASELINE.json configs.
+
+There is no dataset in the build container (and no network), so every workload
+is generated from a fixed seed with numpy and is therefore bit-identical on the
+build box and the GPU box.  The generators follow SURVEY.md section 8(d):
+
+  cfg 1  10k   uniform cube        SH deg 0   256x256    (oracle plumbing)
+  cfg 2  100k  uniform cube        SH deg 0   800x800
+  cfg 3  1M    "bicycle-shaped"    SH deg 3   1600x1200  (headline)
+  cfg 4  5M    "bicycle-shaped"    SH deg 3   1920x1080
+  cfg 5  500k  "bicycle" x0.5      SH deg 3   512x512    (edit loop stand-in)
+
+Camera conventions mirror the reference's ``Simple_Camera``
+(/root/reference/gaussiansplatting/scene/cameras.py:86-94 and
+utils/graphics_utils.py:38-88): ``viewmatrix`` is the TRANSPOSED world-to-camera
+matrix, ``projmatrix`` = viewmatrix @ P^T (also transposed), znear 0.01,
+zfar 100, camera looks down +z.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+SH_C0 = 0.28209479177387814
+
+# Calibration ("calibrate, log, don't tune silently"): with the survey's nominal
+# base scale 0.012 the cfg-3 cloud gives R/V = 21.3 and R/Ntile = 1732 on camera 0 -- outside the
+# target band R/V 6-12, R/Ntile 800-1600 of real Mip-NeRF360 scenes.  0.65 x 0.012 gives
+# R/V = 10.9, R/Ntile = 880 (measured with the CPU oracle), so that is what every config uses.
+BICYCLE_BASE_SCALE = 0.012 * 0.65
+
+
+@dataclass
+class Cloud:
+    """Activated Gaussian parameters, exactly what GaussianRasterizer.forward takes."""
+    means3D: np.ndarray    # [P,3] f32
+    scales: np.ndarray     # [P,3] f32 (already exp-ed)
+    rotations: np.ndarray  # [P,4] f32 (already normalised, r,x,y,z)
+    opacities: np.ndarray  # [P,1] f32 (already sigmoid-ed)
+    shs: np.ndarray        # [P,M,3] f32
+    sh_degree: int
+
+
+@dataclass
+class Camera:
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    viewmatrix: np.ndarray  # [4,4] f32, transposed W2C
+    projmatrix: np.ndarray  # [4,4] f32, transposed full projection
+    campos: np.ndarray      # [3] f32
+
+
+def _projection(znear: float, zfar: float, tanx: float, tany: float) -> np.ndarray:
+    # utils/graphics_utils.py:66-88 (getProjectionMatrix), float32 like the reference.
+    top = tany * znear
+    right = tanx * znear
+    P = np.zeros((4, 4), dtype=np.float32)
+    P[0, 0] = 2.0 * znear / (2.0 * right)
+    P[1, 1] = 2.0 * znear / (2.0 * top)
+    P[3, 2] = 1.0
+    P[2, 2] = zfar / (zfar - znear)
+    P[2, 3] = -(zfar * znear) / (zfar - znear)
+    return P
+
+
+def look_at_camera(eye, target, up, width: int, height: int, *, fovx_deg: float | None = None,
+                   fovy_deg: float | None = None) -> Camera:
+    """Camera at ``eye`` looking at ``target``; exactly one of fovx/fovy is given, the
+    other follows from the aspect ratio with square pixels."""
+    eye = np.asarray(eye, dtype=np.float64)
+    target = np.asarray(target, dtype=np.float64)
+    up = np.asarray(up, dtype=np.float64)
+    fwd = target - eye
+    fwd /= np.linalg.norm(fwd)
+    right = np.cross(up, fwd)
+    right /= np.linalg.norm(right)
+    true_up = np.cross(fwd, right)
+    # world -> camera rotation rows (camera x = right, y = down-ish (true_up), z = forward)
+    Rw2c = np.stack([right, true_up, fwd], axis=0)
+    W2C = np.eye(4, dtype=np.float64)
+    W2C[:3, :3] = Rw2c
+    W2C[:3, 3] = -Rw2c @ eye
+    if fovx_deg is not None:
+        tanx = math.tan(math.radians(fovx_deg) * 0.5)
+        tany = tanx * height / width
+    else:
+        tany = math.tan(math.radians(fovy_deg) * 0.5)
+        tanx = tany * width / height
+    P = _projection(0.01, 100.0, tanx, tany)
+    view_t = np.ascontiguousarray(W2C.astype(np.float32).T)
+    proj_t = np.ascontiguousarray((view_t @ P.T).astype(np.float32))
+    return Camera(height, width, float(tanx), float(tany), view_t, proj_t,
+                  eye.astype(np.float32))
+
+
+def ring_cameras(n: int, radius: float, elevation_deg: float, width: int, height: int,
+                 fovx_deg: float) -> list[Camera]:
+    cams = []
+    el = math.radians(elevation_deg)
+    for k in range(n):
+        az = 2.0 * math.pi * k / n
+        eye = (radius * math.cos(el) * math.cos(az), -radius * math.sin(el),
+               radius * math.cos(el) * math.sin(az))
+        cams.append(look_at_camera(eye, (0, 0, 0), (0, -1, 0), width, height, fovx_deg=fovx_deg))
+    return cams
+
+
+def _random_quats(rng, n):
+    q = rng.standard_normal((n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return q.astype(np.float32)
+
+
+def cube_cloud(P: int, seed: int, log_scale_mean: float, sh_degree: int = 0) -> Cloud:
+    """cfg 1/2: xyz ~ U[-1,1]^3, log-scale ~ N(log s0, 0.4^2), opacity = sigmoid(N(0,2^2))."""
+    rng = np.random.default_rng(seed)
+    M = (sh_degree + 1) ** 2
+    xyz = rng.uniform(-1.0, 1.0, (P, 3)).astype(np.float32)
+    scales = np.exp(rng.normal(math.log(log_scale_mean), 0.4, (P, 3))).astype(np.float32)
+    rot = _random_quats(rng, P)
+    opac = (1.0 / (1.0 + np.exp(-rng.normal(0.0, 2.0, (P, 1))))).astype(np.float32)
+    shs = np.zeros((P, M, 3), dtype=np.float32)
+    shs[:, 0, :] = rng.standard_normal((P, 3)).astype(np.float32)
+    if M > 1:
+        shs[:, 1:, :] = (rng.standard_normal((P, M - 1, 3)) * 0.1).astype(np.float32)
+    return Cloud(xyz, scales, rot, opac, shs, sh_degree)
+
+
+def bicycle_cloud(P: int, seed: int, sh_degree: int = 3, size: float = 1.0) -> Cloud:
+    """cfg 3/4/5: dense core + annulus + far shell mixture."""
+    rng = np.random.default_rng(seed)
+    M = (sh_degree + 1) ** 2
+    n_core = int(0.55 * P)
+    n_ann = int(0.30 * P)
+    n_shell = P - n_core - n_ann
+    core = rng.standard_normal((n_core, 3)) * np.sqrt(np.array([1.5, 0.4, 1.5]))
+    r_a = rng.uniform(3.0, 10.0, n_ann)
+    th = rng.uniform(0.0, 2.0 * math.pi, n_ann)
+    ann = np.stack([r_a * np.cos(th), rng.standard_normal(n_ann), r_a * np.sin(th)], axis=1)
+    r_s = rng.uniform(10.0, 40.0, n_shell)
+    d = rng.standard_normal((n_shell, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:, 1] = -np.abs(d[:, 1])  # upper hemisphere (camera "up" is -y)
+    shell = d * r_s[:, None]
+    xyz = np.concatenate([core, ann, shell], axis=0) * size
+    r = np.linalg.norm(xyz, axis=1) / size
+    base = rng.normal(np.log(BICYCLE_BASE_SCALE * np.maximum(1.0, r / 3.0)), 0.7)
+    logs = base[:, None] + rng.normal(0.0, 0.5, (P, 3))
+    scales = (np.exp(logs) * size).astype(np.float32)
+    rot = _random_quats(rng, P)
+    pick = rng.uniform(size=P) < 0.6
+    logit = np.where(pick, rng.normal(2.0, 1.5, P), rng.normal(-2.0, 1.0, P))
+    opac = (1.0 / (1.0 + np.exp(-logit))).astype(np.float32)[:, None]
+    shs = np.zeros((P, M, 3), dtype=np.float32)
+    shs[:, 0, :] = ((rng.uniform(size=(P, 3)) - 0.5) / SH_C0).astype(np.float32)
+    k = 1
+    for ell in range(1, sh_degree + 1):
+        n = 2 * ell + 1
+        shs[:, k:k + n, :] = (rng.standard_normal((P, n, 3)) * (0.15 / (1 + ell))).astype(np.float32)
+        k += n
+    perm = rng.permutation(P)  # interleave the three populations like a trained scene
+    return Cloud(xyz.astype(np.float32)[perm], scales[perm], rot[perm], opac[perm], shs[perm],
+                 sh_degree)
+
+
+CONFIGS = {
+    # name: (P, sh_degree, W, H)
+    "c1": dict(P=10_000, sh_degree=0, W=256, H=256),
+    "c2": dict(P=100_000, sh_degree=0, W=800, H=800),
+    "c3": dict(P=1_000_000, sh_degree=3, W=1600, H=1200),
+    "c4": dict(P=5_000_000, sh_degree=3, W=1920, H=1080),
+    "c5": dict(P=500_000, sh_degree=3, W=512, H=512),
+}
+
+
+def make_config(name: str, P: int | None = None):
+    """Returns (Cloud, [Camera, ...]) for a BASELINE.json config. ``P`` overrides the
+    Gaussian count (used for bounded CPU samples and small parity cases)."""
+    c = CONFIGS[name]
+    P = c["P"] if P is None else P
+    W, H = c["W"], c["H"]
+    if name == "c1":
+        return cube_cloud(P, 1, 0.03), [look_at_camera((0, 0, -3.5), (0, 0, 0), (0, -1, 0), W, H, fovy_deg=50.0)]
+    if name == "c2":
+        return cube_cloud(P, 2, 0.012), [look_at_camera((0, 0, -3.5), (0, 0, 0), (0, -1, 0), W, H, fovy_deg=50.0)]
+    if name == "c3":
+        return bicycle_cloud(P, 3), ring_cameras(8, 4.5, 15.0, W, H, 61.0)
+    if name == "c4":
+        return bicycle_cloud(P, 4), ring_cameras(8, 4.5, 15.0, W, H, 61.0)
+    if name == "c5":
+        return bicycle_cloud(P, 5, size=0.5), ring_cameras(48, 2.25, 15.0, W, H, 61.0)
+    raise KeyError(name)
