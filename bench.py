@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- forward+backward Mpixels/s of the differentiable Gaussian rasterizer on BASELINE config 3
+(1M synthetic "bicycle-shaped" Gaussians, SH degree 3, 1600x1200), the metric BASELINE.json names.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3]
+
+One "step" = one pass of the hot path over one camera: GaussianRasterizer.forward (preprocess -> depth order
+-> scan -> R read-back -> instance emission -> tile sort -> ranges -> blend, plus output/workspace allocation)
++ autograd backward of loss = (color * G).sum() with a fixed seeded G ~ U(0,1)[3,H,W]  (BASELINE.md timing
+protocol).  The 8 ring cameras of the config are cycled step by step.
+
+  value  : W*H*steps / t / 1e6 with every input resident in HBM before the timed region (CUDA events, max over
+           ranks).  Inputs (236 MB of Gaussian parameters + 192 MB of SH gradients written) exceed the 126 MB
+           L2, so no separate L2 flush is needed between iterations.
+  e2e    : the same step through the public API with HOST buffers: each step copies the camera and the G image
+           from pinned host memory (H2D) and reads the loss back (D2H) inside the timed region.
+  N > 1  : one process per GPU (torchrun), the cloud replicated, every rank renders its own camera stream --
+           the path shards over views with no data-path collective ("weak" scaling); value = all ranks' pixels
+           / max-over-ranks time.
+  --impl reference : the reference's OWN CUDA path (oracle/_ref/libdgr_ref.so = its unmodified .cu files
+           compiled for sm_100a) on the same workload; if that library is absent, the CPU oracle port.
+
+Extra objects on the JSON line: "roofline" (dominant kernel, CUDA-event timed inside this script),
+"cpu_baseline" (CPU oracle on the host cores, rank 0, N=1 only), "stages" (per-stage ms), "workload"
+descriptors (V, R, R/V, R/Ntile, mean n_contrib).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+from gaussianeditor_b200 import synth
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                d = json.load(f)
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def to_dev(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+class Workload:
+    def __init__(self, name, dev, P=None):
+        self.name = name
+        self.cloud, self.cams = synth.make_config(name, P=P)
+        c = self.cloud
+        self.dev = dev
+        self.P = c.means3D.shape[0]
+        self.W, self.H = self.cams[0].image_width, self.cams[0].image_height
+        self.t = dict(means3D=to_dev(c.means3D, dev), opacities=to_dev(c.opacities, dev), shs=to_dev(c.shs, dev),
+                      scales=to_dev(c.scales, dev), rotations=to_dev(c.rotations, dev))
+        self.bg = torch.zeros(3, device=dev)
+        rng = np.random.default_rng(1234)
+        self.G_host = torch.from_numpy(rng.uniform(size=(3, self.H, self.W)).astype(np.float32)).pin_memory()
+        self.G = self.G_host.to(dev)
+        self.cam_host = []
+        for cam in self.cams:
+            blob = np.concatenate([cam.viewmatrix.ravel(), cam.projmatrix.ravel(), cam.campos.ravel(),
+                                   np.zeros(1, np.float32)]).astype(np.float32)
+            self.cam_host.append(torch.from_numpy(blob).pin_memory())
+        self.cam_dev = [b.to(dev) for b in self.cam_host]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ours: through the public drop-in API
+# ---------------------------------------------------------------------------------------------------------
+class OursRunner:
+    impl = "ours"
+
+    def __init__(self, wl: Workload):
+        from gaussianeditor_b200.rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+        self.GRS, self.GR = GaussianRasterizationSettings, GaussianRasterizer
+        self.wl = wl
+        self.leaf = {k: v.clone().requires_grad_(True) for k, v in wl.t.items()}
+        self.means2D = torch.zeros_like(self.leaf["means3D"], requires_grad=True)
+
+    def _settings(self, cam, blob):
+        wl = self.wl
+        return self.GRS(image_height=wl.H, image_width=wl.W, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, bg=wl.bg,
+                        scale_modifier=1.0, viewmatrix=blob[0:16].view(4, 4), projmatrix=blob[16:32].view(4, 4),
+                        sh_degree=wl.cloud.sh_degree, campos=blob[32:35], prefiltered=False, debug=False)
+
+    def step(self, i, host=False):
+        wl, L = self.wl, self.leaf
+        k = i % len(wl.cams)
+        if host:
+            blob = wl.cam_host[k].to(wl.dev, non_blocking=True)
+            G = wl.G_host.to(wl.dev, non_blocking=True)
+        else:
+            blob, G = wl.cam_dev[k], wl.G
+        rast = self.GR(self._settings(wl.cams[k], blob))
+        for v in L.values():
+            v.grad = None
+        self.means2D.grad = None
+        color, radii, depth = rast(means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
+                                   scales=L["scales"], rotations=L["rotations"])
+        loss = (color * G).sum()
+        loss.backward()
+        if host:
+            return float(loss.item())
+        return loss
+
+    def describe(self):
+        from gaussianeditor_b200.rasterizer import _RasterizeGaussians, forward_state_views
+        st = _RasterizeGaussians.last_state
+        v = forward_state_views(st)
+        V = int((st.radii > 0).sum())
+        ntile = v["ranges"].shape[0]
+        return dict(P=st.P, V=V, R=st.num_rendered, R_per_V=st.num_rendered / max(V, 1),
+                    R_per_tile=st.num_rendered / ntile, mean_n_contrib=float(v["n_contrib"].float().mean()),
+                    Ntile=ntile)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference: the reference's own CUDA sources (oracle/_ref) behind its glue restated in oracle/ref_cuda.py
+# ---------------------------------------------------------------------------------------------------------
+class ReferenceCudaRunner:
+    impl = "reference"
+
+    def __init__(self, wl: Workload):
+        from oracle import ref_cuda
+        self.R = ref_cuda.ReferenceRasterizer()
+        self.wl = wl
+
+    def step(self, i, host=False):
+        wl = self.wl
+        k = i % len(wl.cams)
+        cam = wl.cams[k]
+        if host:
+            blob = wl.cam_host[k].to(wl.dev, non_blocking=True)
+            G = wl.G_host.to(wl.dev, non_blocking=True)
+        else:
+            blob, G = wl.cam_dev[k], wl.G
+        common = dict(means3D=wl.t["means3D"], shs=wl.t["shs"], colors_precomp=None, scales=wl.t["scales"],
+                      rotations=wl.t["rotations"], cov3D_precomp=None, bg=wl.bg, viewmatrix=blob[0:16],
+                      projmatrix=blob[16:32], campos=blob[32:35], tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                      sh_degree=wl.cloud.sh_degree)
+        color, radii, depth, R = self.R.forward(opacities=wl.t["opacities"], image_height=wl.H, image_width=wl.W,
+                                                **common)
+        loss = (color * G).sum()
+        # autograd of loss = (color*G).sum() hands dL/dcolor = G to the rasterizer's backward
+        self.g = self.R.backward(dL_dcolor=G, radii=radii, R=R, **common)
+        self.last = (radii, R)
+        if host:
+            return float(loss.item())
+        return loss
+
+    def describe(self):
+        radii, R = self.last
+        V = int((radii > 0).sum())
+        ntile = ((self.wl.W + 15) // 16) * ((self.wl.H + 15) // 16)
+        return dict(P=self.wl.P, V=V, R=int(R), R_per_V=R / max(V, 1), R_per_tile=R / ntile, Ntile=ntile)
+
+
+def cpu_oracle_time(name, P=None, threads=None):
+    """fwd+bwd of one camera of the workload on the CPU oracle (oracle/liboracle_cpu.so, OpenMP)."""
+    from oracle import cpu_oracle
+    cloud, cams = synth.make_config(name, P=P)
+    cam = cams[0]
+    G = np.random.default_rng(1234).uniform(size=(3, cam.image_height, cam.image_width)).astype(np.float32)
+    t0 = time.perf_counter()
+    f = cpu_oracle.forward_from(cloud, cam)
+    g = f.backward(G)
+    dt = time.perf_counter() - t0
+    f.close()
+    return dt, cam.image_width * cam.image_height, cpu_oracle.num_threads()
+
+
+def alg_bytes(desc, M, Msh, W, H):
+    """Compulsory HBM traffic per stage of OUR pipeline (DESIGN.md 'Algorithmic bytes'); bytes."""
+    P, V, R, Nt = desc["P"], desc["V"], desc["R"], desc["Ntile"]
+    npix = W * H
+    return {
+        # in: mean12+scale12+rot16+opacity4 for all P, SH rows only for z-visible; out: record48 (visible) + radii4+tiles4+clamped1+key4+ident4
+        "preprocess_fwd": P * 44 + V * 12 * Msh + V * 48 + P * 17,
+        "depth_order_scan": 4 * (8 + 8) * P + 4 * P + 8 * P + 4 * P,   # 4 radix passes r+w of (key,val) + hist + scan gather/write
+        "emit_instances": P * 8 + V * (16 + 4 + 4) + 8 * R,
+        "tile_sort": (2 * (8 + 8) + 4) * R,                              # 2 passes r+w of (key,val) + histogram read
+        "tile_ranges": 4 * R + 8 * Nt,
+        "render_fwd": (4 + 48) * R + 8 * Nt + 24 * npix,                 # upper bound: whole lists; early-out reads less
+        "render_bwd": (4 + 48) * R + 20 * npix + 36 * R + 48 * P,
+        "preprocess_bwd": P * 5 + V * (48 + 44 + 12 * Msh) + P * (56 + 24 + 12 * M),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3")
+    ap.add_argument("--points", type=int, default=None, help="override the Gaussian count (debug only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    use_cpu_port = False
+    if args.impl == "reference":
+        from oracle import ref_cuda
+        use_cpu_port = not (ref_cuda.available() and torch.cuda.is_available())
+
+    name = args.config
+    cfg = synth.CONFIGS[name]
+    metric = "forward+backward Mpixels/s @1M Gaussians 1600x1200"
+    config = {"workload": f"BASELINE config 3: 1M synthetic bicycle-shaped Gaussians, SH degree 3, 1600x1200, "
+                          f"8 ring cameras cycled, loss=(color*G).sum()" if name == "c3" else f"config {name}",
+              "P": args.points or cfg["P"], "sh_degree": cfg["sh_degree"], "image": [cfg["W"], cfg["H"]],
+              "l2": "inputs (236 MB params + 192 MB SH grads) exceed the 126 MB L2; no explicit flush",
+              "parallelism": f"replicas x{world} (one camera stream per GPU, no data-path collective)"}
+
+    if use_cpu_port:
+        # reference arm without the compiled reference: the CPU oracle port, rank 0 only
+        if rank != 0:
+            return
+        times = []
+        for _ in range(max(1, min(args.steps, 2))):
+            dt, npix, thr = cpu_oracle_time(name, P=args.points)
+            times.append(dt)
+        dt = statistics.median(times)
+        val = npix / dt / 1e6
+        line = {"metric": metric, "value": val, "unit": "Mpixels/s", "n_gpus": 0, "steps": len(times), "warmup": 0,
+                "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": val, "unit": "Mpixels/s", "cores": thr, "kind": "port",
+                                 "sample": "full step (fwd+bwd, camera 0) of the workload"},
+                "e2e": {"value": val, "unit": "Mpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the rasterizer has no CPU fallback "
+                         "(use --impl reference for the CPU oracle port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    wl = Workload(name, dev, P=args.points)
+    runner = OursRunner(wl) if args.impl == "ours" else ReferenceCudaRunner(wl)
+    from gaussianeditor_b200 import _lib
+    npix = wl.W * wl.H
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, host):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            runner.step(i + rank * 3, host=host)
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t[0])
+        return ms
+
+    for i in range(max(args.warmup, 3)):
+        runner.step(i + rank * 3)
+    launches0 = _lib.launch_count() if args.impl == "ours" else 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms = timed(args.steps, host=False)
+    clocks = sampler.stop()
+    launches = (_lib.launch_count() - launches0) if args.impl == "ours" else None
+    for i in range(3):
+        runner.step(i, host=True)
+    ms_e2e = timed(args.steps, host=True)
+    desc = runner.describe()
+
+    value = world * npix * args.steps / (ms * 1e-3) / 1e6
+    e2e = world * npix * args.steps / (ms_e2e * 1e-3) / 1e6
+    line = {"metric": metric, "value": value, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": args.impl,
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "Mpixels/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 3 * npix * 4 + 36 * 4, "d2h_bytes_per_step": 4},
+            "workload": desc}
+
+    if args.impl == "ours":
+        line["gpu_launches"] = int(launches)
+        # per-stage CUDA-event timing (separate pass so the headline is not perturbed)
+        _lib.set_option("profile", 1)
+        _lib.profile_read()
+        nprof = min(args.steps, 16)
+        for i in range(nprof):
+            runner.step(i)
+        prof = _lib.profile_read()
+        _lib.set_option("profile", 0)
+        stages = {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1] > 0}
+        line["stages_ms"] = {k: round(v, 4) for k, v in stages.items()}
+        M = wl.cloud.shs.shape[1]
+        ab = alg_bytes(desc, M, (wl.cloud.sh_degree + 1) ** 2, wl.W, wl.H)
+        dom = max(stages, key=stages.get)
+        peak, peak_src = measured_peaks()
+        ach = ab[dom] / (stages[dom] * 1e-3) / 1e9
+        line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "alg_bytes": ab[dom], "kernel_ms": stages[dom],
+                            "all": {k: {"ms": round(stages[k], 4), "alg_GB": round(ab[k] / 1e9, 4),
+                                        "GBps": round(ab[k] / (stages[k] * 1e-3) / 1e9, 1),
+                                        "frac": round(ab[k] / (stages[k] * 1e-3) / 1e9 / peak, 4)}
+                                    for k in stages if k in ab}}
+    else:
+        line["gpu_launches"] = None
+        line["note"] = "reference CUDA kernels (oracle/_ref), torch glue restated in oracle/ref_cuda.py"
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            dt, npx, thr = cpu_oracle_time(name, P=args.points)
+            line["cpu_baseline"] = {"value": npx / dt / 1e6, "unit": "Mpixels/s", "cores": thr, "kind": "port",
+                                    "sample": "1 full step (fwd+bwd, camera 0) of the workload on the CPU oracle",
+                                    "seconds": dt}
+        except Exception as ex:  # the oracle is a checker; never let it break the bench line
+            line["cpu_baseline"] = {"value": None, "error": str(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

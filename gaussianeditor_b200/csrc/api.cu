@@ -1,0 +1,432 @@
+// C ABI of libgsr_b200.so (include/gsr_b200.h): argument checks, workspace carving, stage orchestration.
+// Orchestration mirrors CudaRasterizer::Rasterizer::{forward,backward,markVisible,apply_weights}
+// (cuda_rasterizer/rasterizer_impl.cu:128-133,179-285,289-341,343-446) with the forward split in two halves
+// around the single host read of num_rendered.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gsr {
+
+Options g_opt;
+long long g_launches = 0;
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return GSR_OK;
+  set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return GSR_ERR_CUDA;
+}
+int check_launch(const char* what, bool debug, cudaStream_t st) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && debug) e = cudaStreamSynchronize(st);
+  return check_cuda(e, what);
+}
+
+struct ProfRec { int stage; cudaEvent_t a, b; };
+static std::vector<ProfRec*> g_prof;
+StageScope::StageScope(int stage_, cudaStream_t st_) : stage(stage_), st(st_), rec(nullptr) {
+  if (!g_opt.profile) return;
+  ProfRec* r = new ProfRec();
+  r->stage = stage;
+  cudaEventCreate(&r->a);
+  cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, st);
+  rec = r;
+}
+StageScope::~StageScope() {
+  if (!rec) return;
+  ProfRec* r = (ProfRec*)rec;
+  cudaEventRecord(r->b, st);
+  g_prof.push_back(r);
+}
+
+static int validate(const gsr_settings* s, const gsr_cloud* c) {
+  if (!s || !c) { set_error("null settings/cloud"); return GSR_ERR_INVALID; }
+  if (c->P < 0 || s->image_width < 0 || s->image_height < 0) { set_error("negative size"); return GSR_ERR_INVALID; }
+  if (c->P > 0 && (!c->means3D || !c->opacities)) { set_error("means3D / opacities must not be null"); return GSR_ERR_INVALID; }
+  // diff_gaussian_rasterization/__init__.py:271-283
+  if ((c->shs == nullptr) == (c->colors_precomp == nullptr)) {
+    set_error("Please provide excatly one of either SHs or precomputed colors!");
+    return GSR_ERR_INVALID;
+  }
+  const bool sr = c->scales != nullptr && c->rotations != nullptr;
+  if (((c->scales == nullptr || c->rotations == nullptr) && c->cov3D_precomp == nullptr) ||
+      ((c->scales != nullptr || c->rotations != nullptr) && c->cov3D_precomp != nullptr)) {
+    set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+    return GSR_ERR_INVALID;
+  }
+  if (sr && (reinterpret_cast<uintptr_t>(c->rotations) & 15)) { set_error("rotations must be 16-byte aligned"); return GSR_ERR_INVALID; }
+  if (c->shs) {
+    if (s->sh_degree < 0 || s->sh_degree > 3 || (s->sh_degree + 1) * (s->sh_degree + 1) > s->sh_coeffs || s->sh_coeffs > 16) {
+      set_error("sh_degree %d needs %d <= sh_coeffs %d <= 16", s->sh_degree, (s->sh_degree + 1) * (s->sh_degree + 1), s->sh_coeffs);
+      return GSR_ERR_INVALID;
+    }
+  }
+  if (!s->bg || !s->viewmatrix || !s->projmatrix || !s->campos) { set_error("camera pointers must not be null"); return GSR_ERR_INVALID; }
+  return GSR_OK;
+}
+
+}  // namespace gsr
+
+using namespace gsr;
+
+extern "C" {
+
+int gsr_abi_version(void) { return GSR_ABI_VERSION; }
+const char* gsr_last_error(void) { return g_err; }
+
+size_t gsr_geometry_bytes(int32_t P) {
+  GeometryWS ws;
+  if (!carve_geometry(nullptr, P, ws)) return 0;
+  return ws.total;
+}
+size_t gsr_image_bytes(int32_t W, int32_t H) {
+  ImageWS ws;
+  carve_image(nullptr, W, H, ws);
+  return ws.total;
+}
+size_t gsr_binning_bytes(int32_t P, int64_t R, int32_t W, int32_t H) {
+  BinningWS ws;
+  if (!carve_binning(nullptr, P, R, W, H, ws)) return 0;
+  return ws.total;
+}
+size_t gsr_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_STRIDE * sizeof(float)); }
+
+int gsr_forward_preprocess(const gsr_settings* s, const gsr_cloud* c, void* geometry, size_t geometry_bytes,
+                           int32_t* radii, int32_t* num_rendered_host, void* stream) {
+  int rc = validate(s, c);
+  if (rc) return rc;
+  if (!num_rendered_host) { set_error("num_rendered_host is null"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->P == 0) { *num_rendered_host = 0; return GSR_OK; }
+  if (!radii || !geometry) { set_error("radii / geometry workspace is null"); return GSR_ERR_INVALID; }
+  GeometryWS g;
+  if (!carve_geometry(geometry, c->P, g)) return GSR_ERR_CUDA;
+  if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
+  {
+    StageScope t(ST_PRE_FWD, st);
+    rc = launch_preprocess_fwd(*s, *c, g, radii, st);
+  }
+  if (rc) return rc;
+  StageScope t(ST_DEPTH_SCAN, st);
+  return run_depth_order_and_scan(*c, g, num_rendered_host, st, s->debug != 0);
+}
+
+static int carve_all(const gsr_settings* s, const gsr_cloud* c, int64_t R, void* geometry, size_t gb, void* binning,
+                     size_t bb, void* image, size_t ib, GeometryWS& g, BinningWS& b, ImageWS& im) {
+  if (!carve_geometry(geometry, c->P, g)) return GSR_ERR_CUDA;
+  if (g.total > gb) { set_error("geometry workspace too small: %zu < %zu", gb, g.total); return GSR_ERR_WORKSPACE; }
+  if (!carve_binning(binning, c->P, R, s->image_width, s->image_height, b)) return GSR_ERR_CUDA;
+  if (R > 0 && (b.total > bb || !binning)) { set_error("binning workspace too small: %zu < %zu", bb, b.total); return GSR_ERR_WORKSPACE; }
+  carve_image(image, s->image_width, s->image_height, im);
+  if (im.total > ib || !image) { set_error("image workspace too small: %zu < %zu", ib, im.total); return GSR_ERR_WORKSPACE; }
+  return GSR_OK;
+}
+
+int gsr_forward_render(const gsr_settings* s, const gsr_cloud* c, int32_t R, void* geometry, size_t geometry_bytes,
+                       void* binning, size_t binning_bytes, void* image, size_t image_bytes, const int32_t* radii,
+                       float* out_color, float* out_depth, void* stream) {
+  int rc = validate(s, c);
+  if (rc) return rc;
+  if (!out_color || !out_depth) { set_error("output images are null"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t npix = (size_t)s->image_width * s->image_height;
+  if (c->P == 0) {  // rasterize_points.cu:72 -- outputs stay zero
+    cudaError_t e = cudaMemsetAsync(out_color, 0, 3 * npix * sizeof(float), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out_depth, 0, npix * sizeof(float), st);
+    return check_cuda(e, "zero outputs");
+  }
+  GeometryWS g; BinningWS b; ImageWS im;
+  rc = carve_all(s, c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, g, b, im);
+  if (rc) return rc;
+  rc = run_binning(*s, *c, R, g, b, im, radii, st);
+  if (rc) return rc;
+  StageScope t(ST_RENDER_FWD, st);
+  return launch_render_fwd(*s, g, b, im, out_color, out_depth, st);
+}
+
+int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
+                 const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
+                 const int32_t* radii, const float* dL_dout_color, void* scratch, size_t scratch_bytes,
+                 const gsr_grads* gr, void* stream) {
+  int rc = validate(s, c);
+  if (rc) return rc;
+  if (!gr || !dL_dout_color) { set_error("grads / dL_dout_color is null"); return GSR_ERR_INVALID; }
+  if (c->P == 0) return GSR_OK;
+  if (!gr->dL_dmeans3D || !gr->dL_dmeans2D || !gr->dL_dcolors || !gr->dL_dopacity || !gr->dL_dcov3D ||
+      !gr->dL_dscales || !gr->dL_drotations || (c->shs && !gr->dL_dsh)) {
+    set_error("a gradient output pointer is null");
+    return GSR_ERR_INVALID;
+  }
+  if (reinterpret_cast<uintptr_t>(gr->dL_drotations) & 15) { set_error("dL_drotations must be 16-byte aligned"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  GeometryWS g; BinningWS b; ImageWS im;
+  rc = carve_all(s, c, R, const_cast<void*>(geometry), geometry_bytes, const_cast<void*>(binning), binning_bytes,
+                 const_cast<void*>(image), image_bytes, g, b, im);
+  if (rc) return rc;
+  const size_t need = gsr_backward_scratch_bytes(c->P);
+  if (!scratch || scratch_bytes < need) { set_error("backward scratch too small: %zu < %zu", scratch_bytes, need); return GSR_ERR_WORKSPACE; }
+  {
+    StageScope t(ST_RENDER_BWD, st);  // includes zeroing the accumulators
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)c->P * ACC_STRIDE * sizeof(float), st);
+    if (e != cudaSuccess) return check_cuda(e, "scratch memset");
+    if (R > 0) {
+      rc = launch_render_bwd(*s, g, b, im, dL_dout_color, (float*)scratch, st);
+      if (rc) return rc;
+    }
+  }
+  StageScope t(ST_PRE_BWD, st);
+  return launch_preprocess_bwd(*s, *c, g, radii, (const float*)scratch, *gr, st);
+}
+
+int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream) {
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) { set_error("mark_visible: bad arguments"); return GSR_ERR_INVALID; }
+  if (P == 0) return GSR_OK;
+  return launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream);
+}
+
+int gsr_apply_weights(const gsr_settings* s, const gsr_cloud* c, int32_t R, void* geometry, size_t geometry_bytes,
+                      void* binning, size_t binning_bytes, void* image, size_t image_bytes, const int32_t* radii,
+                      const float* image_weights, int32_t CH, float* weights, int32_t* cnt, void* stream) {
+  int rc = validate(s, c);
+  if (rc) return rc;
+  if (!image_weights || !weights || !cnt) { set_error("apply_weights: null buffer"); return GSR_ERR_INVALID; }
+  if (c->P == 0 || R <= 0) return GSR_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  GeometryWS g; BinningWS b; ImageWS im;
+  rc = carve_all(s, c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, g, b, im);
+  if (rc) return rc;
+  rc = run_binning(*s, *c, R, g, b, im, radii, st);
+  if (rc) return rc;
+  StageScope t(ST_APPLY_W, st);
+  return launch_apply_weights(*s, g, b, im, image_weights, CH, weights, cnt, st);
+}
+
+int gsr_view_geometry(const void* geometry, int32_t P, gsr_geometry_view* out) {
+  GeometryWS g;
+  if (!out || !carve_geometry(const_cast<void*>(geometry), P, g)) return GSR_ERR_INVALID;
+  out->records = (const float*)g.records; out->tiles_touched = g.tiles_touched; out->clamped = g.clamped;
+  out->depth_order = g.depth_order;
+  return GSR_OK;
+}
+int gsr_view_binning(const void* binning, int32_t P, int64_t R, int32_t W, int32_t H, gsr_binning_view* out) {
+  BinningWS b;
+  if (!out || !carve_binning(const_cast<void*>(binning), P, R, W, H, b)) return GSR_ERR_INVALID;
+  out->point_list = b.point_list; out->tile_keys = b.keys_sorted;
+  return GSR_OK;
+}
+int gsr_view_image(const void* image, int32_t W, int32_t H, gsr_image_view* out) {
+  ImageWS im;
+  if (!out) return GSR_ERR_INVALID;
+  carve_image(const_cast<void*>(image), W, H, im);
+  out->final_T = im.final_T; out->n_contrib = im.n_contrib; out->ranges = (const uint32_t*)im.ranges;
+  return GSR_OK;
+}
+
+int gsr_set_option(const char* name, int64_t value) {
+  if (!name) return GSR_ERR_INVALID;
+  if (!strcmp(name, "render_fwd_variant")) g_opt.render_fwd_variant = (int)value;
+  else if (!strcmp(name, "render_bwd_variant")) g_opt.render_bwd_variant = (int)value;
+  else if (!strcmp(name, "preprocess_variant")) g_opt.preprocess_variant = (int)value;
+  else if (!strcmp(name, "profile")) g_opt.profile = (int)value;
+  else { set_error("unknown option %s", name); return GSR_ERR_INVALID; }
+  return GSR_OK;
+}
+int64_t gsr_get_option(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "render_fwd_variant")) return g_opt.render_fwd_variant;
+  if (!strcmp(name, "render_bwd_variant")) return g_opt.render_bwd_variant;
+  if (!strcmp(name, "preprocess_variant")) return g_opt.preprocess_variant;
+  if (!strcmp(name, "profile")) return g_opt.profile;
+  return -1;
+}
+int64_t gsr_launch_count(void) { return g_launches; }
+
+int gsr_profile_read(double* ms_out, int64_t* calls_out) {
+  if (!ms_out || !calls_out) return GSR_ERR_INVALID;
+  for (int i = 0; i < GSR_NUM_STAGES; i++) { ms_out[i] = 0.0; calls_out[i] = 0; }
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return check_cuda(e, "profile_read");
+  for (ProfRec* r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r->a, r->b) == cudaSuccess && r->stage >= 0 && r->stage < GSR_NUM_STAGES) {
+      ms_out[r->stage] += ms;
+      calls_out[r->stage]++;
+    }
+    cudaEventDestroy(r->a);
+    cudaEventDestroy(r->b);
+    delete r;
+  }
+  g_prof.clear();
+  return GSR_OK;
+}
+
+}  // extern "C"
+
+// ---- host-buffer convenience API -----------------------------------------------------------------------
+struct gsr_host_ctx {
+  int P = 0, M = 0;
+  float *means3D = nullptr, *opac = nullptr, *shs = nullptr, *scales = nullptr, *rots = nullptr;
+  float* cam = nullptr;  // bg[3] pad, view[16], proj[16], campos[3]: 40 floats
+  void *geom = nullptr, *bin = nullptr, *img = nullptr, *scratch = nullptr;
+  size_t geom_b = 0, bin_b = 0, img_b = 0, scratch_b = 0;
+  int32_t* radii = nullptr;
+  float *out_color = nullptr, *out_depth = nullptr, *dL = nullptr;
+  size_t img_cap = 0;
+  float* grads = nullptr;  // all gradient tensors, contiguous
+  size_t grads_cap = 0;
+  double* sums = nullptr;
+  int32_t* R_pinned = nullptr;
+  float* cam_pinned = nullptr;
+  cudaStream_t st = nullptr;
+};
+
+namespace {
+__global__ void checksum_kernel(const float* __restrict__ x, size_t n, double* out) {
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += x[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+template <typename T> int dev_alloc(T** p, size_t n) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  return check_cuda(cudaMalloc((void**)p, n ? n : 1), "cudaMalloc");
+}
+}  // namespace
+
+extern "C" {
+
+gsr_host_ctx* gsr_host_create(void) {
+  gsr_host_ctx* c = new gsr_host_ctx();
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMallocHost((void**)&c->R_pinned, sizeof(int32_t)) != cudaSuccess ||
+      cudaMallocHost((void**)&c->cam_pinned, 40 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&c->cam, 40 * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&c->sums, 8 * sizeof(double)) != cudaSuccess) {
+    check_cuda(cudaGetLastError(), "gsr_host_create");
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+void gsr_host_destroy(gsr_host_ctx* c) {
+  if (!c) return;
+  void* ptrs[] = {c->means3D, c->opac, c->shs, c->scales, c->rots, c->cam, c->geom, c->bin, c->img, c->scratch,
+                  c->radii, c->out_color, c->out_depth, c->dL, c->grads, c->sums};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (c->R_pinned) cudaFreeHost(c->R_pinned);
+  if (c->cam_pinned) cudaFreeHost(c->cam_pinned);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+int gsr_host_upload_cloud(gsr_host_ctx* c, int32_t P, int32_t M, const float* means3D, const float* opacities,
+                          const float* shs, const float* scales, const float* rotations) {
+  if (!c || P <= 0 || M <= 0 || !means3D || !opacities || !shs || !scales || !rotations) { set_error("upload_cloud: bad arguments"); return GSR_ERR_INVALID; }
+  c->P = P; c->M = M;
+  int rc;
+  if ((rc = dev_alloc(&c->means3D, (size_t)P * 12))) return rc;
+  if ((rc = dev_alloc(&c->opac, (size_t)P * 4))) return rc;
+  if ((rc = dev_alloc(&c->shs, (size_t)P * M * 12))) return rc;
+  if ((rc = dev_alloc(&c->scales, (size_t)P * 12))) return rc;
+  if ((rc = dev_alloc(&c->rots, (size_t)P * 16))) return rc;
+  if ((rc = dev_alloc(&c->radii, (size_t)P * 4))) return rc;
+  cudaMemcpyAsync(c->means3D, means3D, (size_t)P * 12, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(c->opac, opacities, (size_t)P * 4, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(c->shs, shs, (size_t)P * M * 12, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(c->scales, scales, (size_t)P * 12, cudaMemcpyHostToDevice, c->st);
+  cudaMemcpyAsync(c->rots, rotations, (size_t)P * 16, cudaMemcpyHostToDevice, c->st);
+  c->geom_b = gsr_geometry_bytes(P);
+  if ((rc = dev_alloc((char**)&c->geom, c->geom_b))) return rc;
+  c->scratch_b = gsr_backward_scratch_bytes(P);
+  if ((rc = dev_alloc((char**)&c->scratch, c->scratch_b))) return rc;
+  const size_t gn = (size_t)P * (3 + 3 + 3 + 1 + 6 + 3 * (size_t)M + 3 + 4);
+  if ((rc = dev_alloc(&c->grads, gn * 4 + 256))) return rc;
+  c->grads_cap = gn;
+  return check_cuda(cudaStreamSynchronize(c->st), "upload_cloud");
+}
+
+int64_t gsr_host_step(gsr_host_ctx* c, const gsr_settings* sh, const float* dL_host, float* out_color_host,
+                      int32_t* out_radii_host, double* sums_host) {
+  if (!c || !sh || c->P <= 0) { set_error("host_step: no cloud uploaded"); return GSR_ERR_INVALID; }
+  const int W = sh->image_width, H = sh->image_height, P = c->P, M = c->M;
+  const size_t npix = (size_t)W * H;
+  int rc;
+  if (npix > c->img_cap) {
+    if ((rc = dev_alloc(&c->out_color, npix * 12))) return rc;
+    if ((rc = dev_alloc(&c->out_depth, npix * 4))) return rc;
+    if ((rc = dev_alloc(&c->dL, npix * 12))) return rc;
+    c->img_b = gsr_image_bytes(W, H);
+    if ((rc = dev_alloc((char**)&c->img, c->img_b))) return rc;
+    c->img_cap = npix;
+  }
+  // camera: host -> pinned -> device
+  memcpy(c->cam_pinned, sh->bg, 12);
+  memcpy(c->cam_pinned + 4, sh->viewmatrix, 64);
+  memcpy(c->cam_pinned + 20, sh->projmatrix, 64);
+  memcpy(c->cam_pinned + 36, sh->campos, 12);
+  cudaMemcpyAsync(c->cam, c->cam_pinned, 160, cudaMemcpyHostToDevice, c->st);
+  gsr_settings s = *sh;
+  s.bg = c->cam; s.viewmatrix = c->cam + 4; s.projmatrix = c->cam + 20; s.campos = c->cam + 36;
+  s.sh_coeffs = M;
+  gsr_cloud cl;
+  cl.P = P; cl.means3D = c->means3D; cl.opacities = c->opac; cl.shs = c->shs; cl.colors_precomp = nullptr;
+  cl.scales = c->scales; cl.rotations = c->rots; cl.cov3D_precomp = nullptr;
+  if (dL_host) cudaMemcpyAsync(c->dL, dL_host, npix * 12, cudaMemcpyHostToDevice, c->st);
+  rc = gsr_forward_preprocess(&s, &cl, c->geom, c->geom_b, c->radii, c->R_pinned, c->st);
+  if (rc) return rc;
+  if ((rc = check_cuda(cudaStreamSynchronize(c->st), "host_step sync"))) return rc;
+  const int R = *c->R_pinned;
+  const size_t need = gsr_binning_bytes(P, R, W, H);
+  if (need > c->bin_b) {
+    c->bin_b = need + need / 4;
+    if ((rc = dev_alloc((char**)&c->bin, c->bin_b))) return rc;
+  }
+  rc = gsr_forward_render(&s, &cl, R, c->geom, c->geom_b, c->bin, c->bin_b, c->img, c->img_b, c->radii, c->out_color,
+                          c->out_depth, c->st);
+  if (rc) return rc;
+  if (out_color_host) cudaMemcpyAsync(out_color_host, c->out_color, npix * 12, cudaMemcpyDeviceToHost, c->st);
+  if (out_radii_host) cudaMemcpyAsync(out_radii_host, c->radii, (size_t)P * 4, cudaMemcpyDeviceToHost, c->st);
+  if (dL_host) {
+    float* p = c->grads;
+    gsr_grads gr;
+    gr.dL_drotations = p; p += (size_t)P * 4;  // first: keeps 16-byte alignment
+    gr.dL_dsh = p; p += (size_t)P * M * 3;
+    gr.dL_dmeans3D = p; p += (size_t)P * 3;
+    gr.dL_dmeans2D = p; p += (size_t)P * 3;
+    gr.dL_dcolors = p; p += (size_t)P * 3;
+    gr.dL_dopacity = p; p += (size_t)P;
+    gr.dL_dcov3D = p; p += (size_t)P * 6;
+    gr.dL_dscales = p; p += (size_t)P * 3;
+    rc = gsr_backward(&s, &cl, R, c->geom, c->geom_b, c->bin, c->bin_b, c->img, c->img_b, c->radii, c->dL, c->scratch,
+                      c->scratch_b, &gr, c->st);
+    if (rc) return rc;
+    if (sums_host) {
+      cudaMemsetAsync(c->sums, 0, 8 * sizeof(double), c->st);
+      const float* ptrs[8] = {gr.dL_dmeans3D, gr.dL_dmeans2D, gr.dL_dcolors, gr.dL_dopacity,
+                              gr.dL_dcov3D, gr.dL_dsh, gr.dL_dscales, gr.dL_drotations};
+      const size_t ns[8] = {(size_t)P * 3, (size_t)P * 3, (size_t)P * 3, (size_t)P, (size_t)P * 6, (size_t)P * M * 3, (size_t)P * 3, (size_t)P * 4};
+      for (int i = 0; i < 8; i++) {
+        checksum_kernel<<<296, 256, 0, c->st>>>(ptrs[i], ns[i], c->sums + i);
+        g_launches++;
+      }
+      cudaMemcpyAsync(sums_host, c->sums, 8 * sizeof(double), cudaMemcpyDeviceToHost, c->st);
+    }
+  }
+  if ((rc = check_cuda(cudaStreamSynchronize(c->st), "host_step end"))) return rc;
+  return R;
+}
+
+}  // extern "C"

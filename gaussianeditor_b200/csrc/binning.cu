@@ -1,0 +1,263 @@
+// Binning for sm_100a: turn per-Gaussian tile rectangles into per-tile, depth-ordered splat lists.
+//
+// The reference (cuda_rasterizer/rasterizer_impl.cu:227-270) emits one 64-bit key  tile<<32 | depth_bits  per
+// (Gaussian, tile) instance in Gaussian-index order and radix-sorts all R instances over 32+bit key bits
+// (6 eight-bit passes over 12 B/instance).  Its result -- point_list and the tile ranges -- is fully
+// determined by the order  (tile, depth bits, Gaussian index)  because the sort is stable.
+//
+// Here the same permutation is produced with a quarter of the traffic by splitting the key:
+//   1. stable radix sort of the P Gaussians by depth bits (32-bit keys, P items, culled ones keyed 0xFFFFFFFF),
+//   2. inclusive scan of the tile counts IN THAT ORDER -> instance offsets, R,
+//   3. emission of (tile id, Gaussian index) in depth order (warp-cooperative for large rectangles),
+//   4. stable radix sort of the R instances by tile id only (`bit` = getHigherMsb(Ntile) bits -> 2 passes over
+//      8 B/instance) -- ties keep emission order = (depth bits, index),
+//   5. tile ranges from the sorted tile ids.
+// Equality of point_list / ranges / R with the reference is asserted bit-for-bit in the GPU tests.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace gsr {
+
+namespace {
+
+// rasterizer_impl.cu:36-49 (number of key bits that cover the tile ids)
+uint32_t higher_msb(uint32_t n) {
+  uint32_t msb = sizeof(n) * 4;
+  uint32_t step = msb;
+  while (step > 1) {
+    step /= 2;
+    if (n >> msb)
+      msb += step;
+    else
+      msb -= step;
+  }
+  if (n >> msb) msb++;
+  return msb;
+}
+
+// tiles_touched gathered through the depth order, as a CUB input iterator
+struct GatherTilesOp {
+  const uint32_t* tiles;
+  const uint32_t* order;
+  __host__ __device__ __forceinline__ uint32_t operator()(uint32_t rank) const { return tiles[order[rank]]; }
+};
+
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx, int gy, uint2& rmin, uint2& rmax) {
+  // auxiliary.h:46-56
+  rmin.x = (unsigned)min(gx, max((int)0, (int)((px - radius) / TILE)));
+  rmin.y = (unsigned)min(gy, max((int)0, (int)((py - radius) / TILE)));
+  rmax.x = (unsigned)min(gx, max((int)0, (int)((px + radius + TILE - 1) / TILE)));
+  rmax.y = (unsigned)min(gy, max((int)0, (int)((py + radius + TILE - 1) / TILE)));
+}
+
+// One warp per 32 consecutive depth ranks. Small rectangles are written by their own lane; rectangles with
+// more than SMALL tiles are written by the whole warp with coalesced stores (a single huge foreground splat
+// can cover thousands of tiles and would otherwise serialise one thread).
+constexpr int EMIT_THREADS = 256;
+constexpr int SMALL = 8;
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
+                      const uint32_t* __restrict__ tiles_touched, const SplatRecord* __restrict__ records,
+                      const int32_t* __restrict__ radii, int gx, int gy, uint32_t* __restrict__ keys,
+                      uint32_t* __restrict__ vals) {
+  const int rank = blockIdx.x * EMIT_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  uint32_t idx = 0, n = 0, end = 0;
+  uint2 rmin = make_uint2(0, 0), rmax = make_uint2(0, 0);
+  if (rank < P) {
+    idx = order[rank];
+    n = tiles_touched[idx];
+    if (n > 0) {
+      end = offsets[rank];
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(records + idx));
+      tile_rect(q0.x, q0.y, radii[idx], gx, gy, rmin, rmax);
+    }
+  }
+  uint32_t off = end - n;
+  if (n > 0 && n <= SMALL) {
+    for (uint32_t y = rmin.y; y < rmax.y; y++)
+      for (uint32_t x = rmin.x; x < rmax.x; x++) {
+        keys[off] = y * gx + x;
+        vals[off] = idx;
+        off++;
+      }
+  }
+  unsigned big = __ballot_sync(0xffffffffu, n > SMALL);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const uint32_t b_idx = __shfl_sync(0xffffffffu, idx, src);
+    const uint32_t b_n = __shfl_sync(0xffffffffu, n, src);
+    const uint32_t b_off = __shfl_sync(0xffffffffu, off, src);
+    const uint32_t b_x0 = __shfl_sync(0xffffffffu, rmin.x, src);
+    const uint32_t b_y0 = __shfl_sync(0xffffffffu, rmin.y, src);
+    const uint32_t b_w = __shfl_sync(0xffffffffu, rmax.x - rmin.x, src);
+    for (uint32_t k = lane; k < b_n; k += 32) {
+      const uint32_t ry = k / b_w, rx = k - ry * b_w;
+      keys[b_off + k] = (b_y0 + ry) * gx + (b_x0 + rx);
+      vals[b_off + k] = b_idx;
+    }
+  }
+}
+
+// rasterizer_impl.cu:105-125 on 32-bit tile keys; ranges must be zeroed beforehand (:263-265)
+__global__ void tile_ranges_kernel(int L, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= L) return;
+  const uint32_t cur = keys[idx];
+  if (idx == 0)
+    ranges[cur].x = 0;
+  else {
+    const uint32_t prev = keys[idx - 1];
+    if (cur != prev) {
+      ranges[prev].y = idx;
+      ranges[cur].x = idx;
+    }
+  }
+  if (idx == L - 1) ranges[cur].y = L;
+}
+
+size_t depth_sort_temp_bytes(int P) {
+  size_t n = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, P);
+  return n;
+}
+size_t scan_temp_bytes(int P) {
+  size_t n = 0;
+  cub::TransformInputIterator<uint32_t, GatherTilesOp, cub::CountingInputIterator<uint32_t>> it(
+      cub::CountingInputIterator<uint32_t>(0), GatherTilesOp{nullptr, nullptr});
+  cub::DeviceScan::InclusiveSum(nullptr, n, it, (uint32_t*)nullptr, P);
+  return n;
+}
+size_t tile_sort_temp_bytes(int64_t R) {
+  size_t n = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)R, 0, 32);
+  return n;
+}
+
+}  // namespace
+
+bool carve_geometry(void* base, int P, GeometryWS& ws) {
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* p = b ? (void*)(b + off) : nullptr;
+    off += align_up(bytes ? bytes : 1);
+    return p;
+  };
+  const size_t n = (size_t)(P > 0 ? P : 1);
+  ws.records = (SplatRecord*)take(n * sizeof(SplatRecord));
+  ws.tiles_touched = (uint32_t*)take(n * 4);
+  ws.clamped = (uint8_t*)take(n);
+  ws.depth_keys = (uint32_t*)take(n * 4);
+  ws.ident = (uint32_t*)take(n * 4);
+  ws.depth_keys_sorted = (uint32_t*)take(n * 4);
+  ws.depth_order = (uint32_t*)take(n * 4);
+  ws.offsets = (uint32_t*)take(n * 4);
+  size_t t1 = depth_sort_temp_bytes((int)n), t2 = scan_temp_bytes((int)n);
+  if (cudaPeekAtLastError() != cudaSuccess) {
+    check_cuda(cudaGetLastError(), "CUB temp-size query");
+    return false;
+  }
+  ws.cub_temp_bytes = t1 > t2 ? t1 : t2;
+  ws.cub_temp = take(ws.cub_temp_bytes);
+  ws.total = off;
+  return true;
+}
+
+bool carve_binning(void* base, int P, int64_t R, int W, int H, BinningWS& ws) {
+  (void)P; (void)W; (void)H;
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* p = b ? (void*)(b + off) : nullptr;
+    off += align_up(bytes ? bytes : 1);
+    return p;
+  };
+  const size_t n = (size_t)(R > 0 ? R : 1);
+  ws.keys_unsorted = (uint32_t*)take(n * 4);
+  ws.keys_sorted = (uint32_t*)take(n * 4);
+  ws.vals_unsorted = (uint32_t*)take(n * 4);
+  ws.point_list = (uint32_t*)take(n * 4);
+  ws.cub_temp_bytes = tile_sort_temp_bytes((int64_t)n);
+  if (cudaPeekAtLastError() != cudaSuccess) {
+    check_cuda(cudaGetLastError(), "CUB temp-size query");
+    return false;
+  }
+  ws.cub_temp = take(ws.cub_temp_bytes);
+  ws.total = off;
+  return true;
+}
+
+void carve_image(void* base, int W, int H, ImageWS& ws) {
+  size_t off = 0;
+  char* b = (char*)base;
+  auto take = [&](size_t bytes) {
+    void* p = b ? (void*)(b + off) : nullptr;
+    off += align_up(bytes ? bytes : 1);
+    return p;
+  };
+  const size_t npix = (size_t)W * H;
+  const size_t ntile = (size_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE);
+  ws.final_T = (float*)take(npix * 4);
+  ws.n_contrib = (uint32_t*)take(npix * 4);
+  ws.ranges = (uint2*)take(ntile * 8);
+  ws.tile_last = (uint32_t*)take(ntile * 4);
+  ws.total = off;
+}
+
+int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
+                             bool debug) {
+  const int P = c.P;
+  size_t tb = g.cub_temp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, (const uint32_t*)g.depth_keys, g.depth_keys_sorted,
+                                                  (const uint32_t*)g.ident, g.depth_order, P, 0, 32, st);
+  g_launches += 5;
+  if (e != cudaSuccess) return check_cuda(e, "depth sort");
+  cub::TransformInputIterator<uint32_t, GatherTilesOp, cub::CountingInputIterator<uint32_t>> it(
+      cub::CountingInputIterator<uint32_t>(0), GatherTilesOp{g.tiles_touched, g.depth_order});
+  tb = g.cub_temp_bytes;
+  e = cub::DeviceScan::InclusiveSum(g.cub_temp, tb, it, g.offsets, P, st);
+  g_launches += 2;
+  if (e != cudaSuccess) return check_cuda(e, "tile-count scan");
+  e = cudaMemcpyAsync(num_rendered_host, g.offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess) return check_cuda(e, "num_rendered readback");
+  return check_launch("depth order + scan", debug, st);
+}
+
+int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, const GeometryWS& g, const BinningWS& b,
+                const ImageWS& im, const int32_t* radii, cudaStream_t st) {
+  const int W = s.image_width, H = s.image_height;
+  const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
+  const bool debug = s.debug != 0;
+  cudaError_t e = cudaMemsetAsync(im.ranges, 0, (size_t)gx * gy * sizeof(uint2), st);
+  if (e != cudaSuccess) return check_cuda(e, "ranges memset");
+  if (R <= 0) return GSR_OK;
+  int rc;
+  {
+    StageScope t(ST_EMIT, st);
+    emit_instances_kernel<<<(c.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(
+        c.P, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, b.keys_unsorted, b.vals_unsorted);
+    g_launches++;
+    rc = check_launch("emit_instances", debug, st);
+    if (rc) return rc;
+  }
+  {
+    StageScope t(ST_TILE_SORT, st);
+    const int bit = (int)higher_msb((uint32_t)(gx * gy));
+    size_t tb = b.cub_temp_bytes;
+    e = cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, (const uint32_t*)b.keys_unsorted, b.keys_sorted,
+                                        (const uint32_t*)b.vals_unsorted, b.point_list, R, 0, bit, st);
+    g_launches += 4;
+    if (e != cudaSuccess) return check_cuda(e, "tile sort");
+  }
+  StageScope t(ST_RANGES, st);
+  tile_ranges_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, b.keys_sorted, im.ranges);
+  g_launches++;
+  return check_launch("tile_ranges", debug, st);
+}
+
+}  // namespace gsr

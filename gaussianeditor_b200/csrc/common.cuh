@@ -1,0 +1,168 @@
+// Shared declarations of the sm_100a rasterizer kernels (internal; the public surface is include/gsr_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/gsr_b200.h"
+
+namespace gsr {
+
+constexpr int TILE = 16;  // tile edge in pixels; fixed by the reference's binning (config.h:16-17) and
+                          // therefore by the bit-exact tile-range contract
+constexpr int TILE_PIX = TILE * TILE;
+
+// ---- HBM layout ------------------------------------------------------------------------------------
+// Per-Gaussian "splat record": everything the two render kernels need about a projected Gaussian, packed
+// into 48 contiguous, 16-byte-aligned bytes so that one tile-list gather is three 128-bit loads
+// (the reference gathers from five separate arrays: means2D, conic_opacity, rgb, depths, point ids).
+//   q0 = { x, y, conic.a, conic.b }      q1 = { conic.c, opacity, view-depth, <unused> }
+//   q2 = { r, g, b, <unused> }
+struct __align__(16) SplatRecord {
+  float4 q0, q1, q2;
+};
+static_assert(sizeof(SplatRecord) == 48, "record layout");
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct GeometryWS {
+  SplatRecord* records;     // [P]
+  uint32_t* tiles_touched;  // [P]
+  uint8_t* clamped;         // [P]
+  uint32_t* depth_keys;     // [P] fp32 view-depth bits, 0xFFFFFFFF for culled
+  uint32_t* ident;          // [P] 0..P-1
+  uint32_t* depth_keys_sorted;
+  uint32_t* depth_order;    // [P] Gaussian indices in (depth, index) order
+  uint32_t* offsets;        // [P] inclusive scan of tiles_touched in depth order
+  void* cub_temp;
+  size_t cub_temp_bytes;
+  size_t total;
+};
+struct BinningWS {
+  uint32_t* keys_unsorted;  // [R] tile id
+  uint32_t* keys_sorted;    // [R]
+  uint32_t* vals_unsorted;  // [R] Gaussian index
+  uint32_t* point_list;     // [R] sorted
+  void* cub_temp;
+  size_t cub_temp_bytes;
+  size_t total;
+};
+struct ImageWS {
+  float* final_T;       // [Npix]
+  uint32_t* n_contrib;  // [Npix]
+  uint2* ranges;        // [Ntile]
+  uint32_t* tile_last;  // [Ntile] max n_contrib over the tile's pixels: where the backward walk starts
+  size_t total;
+};
+
+// Carve a workspace out of `base` (may be null for a pure size query).
+bool carve_geometry(void* base, int P, GeometryWS& ws);
+bool carve_binning(void* base, int P, int64_t R, int W, int H, BinningWS& ws);
+void carve_image(void* base, int W, int H, ImageWS& ws);
+
+// Backward scratch: per-Gaussian accumulators of the nine 2-D gradients (+3 pad -> 48 B, 16-B aligned):
+//   [0..2] dL/dcolor  [3..4] dL/dmean2D  [5..7] dL/dconic (a,b,c)  [8] dL/dopacity
+constexpr int ACC_STRIDE = 12;
+
+// ---- options -----------------------------------------------------------------------------------------
+struct Options {
+  int render_fwd_variant = 1;
+  int render_bwd_variant = 1;
+  int preprocess_variant = 1;
+  int profile = 0;
+};
+enum Stage { ST_PRE_FWD = 0, ST_DEPTH_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_RENDER_FWD, ST_RENDER_BWD, ST_PRE_BWD, ST_APPLY_W };
+// RAII stage timer: records two events on `st` when profiling is on, otherwise free.
+struct StageScope {
+  int stage; cudaStream_t st; void* rec;
+  StageScope(int stage, cudaStream_t st);
+  ~StageScope();
+};
+extern Options g_opt;
+extern long long g_launches;
+
+// ---- error plumbing ------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int check_launch(const char* what, bool debug, cudaStream_t st);
+
+// ---- stage entry points (host side; each file owns its kernels) ------------------------------------------
+int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
+                          cudaStream_t st);
+int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
+                             bool debug);
+int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, const GeometryWS& g, const BinningWS& b,
+                const ImageWS& im, const int32_t* radii, cudaStream_t st);
+int launch_render_fwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
+                      float* out_color, float* out_depth, cudaStream_t st);
+int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
+                      const float* dL_dpix, float* acc, cudaStream_t st);
+int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
+                          const float* acc, const gsr_grads& gr, cudaStream_t st);
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
+int launch_apply_weights(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
+                         const float* image_weights, int CH, float* weights, int32_t* cnt, cudaStream_t st);
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------------
+
+// Reference numerics of one (pixel, splat) evaluation, fixed with explicit round-to-nearest intrinsics so the
+// compiler can neither re-associate nor contract differently. The sequence is what nvcc emits for
+// forward.cu:335-338 / backward.cu:491-494 at sm_100a (SASS of the unmodified reference):
+//   power = fma( fma(dx, A*dx, (C*dy)*dy), -0.5, -((B*dx)*dy) )
+__device__ __forceinline__ float splat_power(float dx, float dy, float A, float B, float C) {
+  float t0 = __fmul_rn(__fmul_rn(dy, C), dy);
+  float t1 = __fmul_rn(dx, A);
+  float t2 = __fmul_rn(__fmul_rn(dx, B), dy);
+  float s = __fmaf_rn(dx, t1, t0);
+  return __fmaf_rn(s, -0.5f, -t2);
+}
+
+// 128-bit streaming loads/stores
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// mbarrier + bulk async copy (TMA unit; SASS: UBLKCP / SYNCS)
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(phase)
+      : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar`; size and both addresses multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif  // __CUDACC__
+
+}  // namespace gsr

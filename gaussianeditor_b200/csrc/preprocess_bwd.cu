@@ -1,0 +1,398 @@
+// Backward of the per-Gaussian preprocess for sm_100a: 2-D gradients -> gradients of means3D, scales,
+// rotations (or cov3D), SH coefficients (or colours) and opacity.
+//
+// Semantics: the reference's two kernels computeCov2DCUDA (cuda_rasterizer/backward.cu:144-274) and
+// preprocessCUDA (bwd, :346-396 with computeColorFromSH :20-139 and computeCov3D :278-341), in the order of
+// rasterizer_impl.cu:333-340 (the covariance kernel ASSIGNS dL/dmean, the second kernel adds the projection and
+// SH view-direction terms).  Fused here into ONE pass over the cloud:
+//   * every input byte of a Gaussian is read once (the reference reads mean/radii/cov3D twice and round-trips
+//     dL/dcov3D and dL/dmean through HBM between its two kernels); cov3D is recomputed from scale/rotation
+//     instead of being stored by the forward (saves 24 B/Gaussian written + read);
+//   * the kernel writes EVERY gradient element itself -- zeros for culled Gaussians and for SH coefficients
+//     above the active degree -- so the caller allocates outputs uninitialised and the reference's nine
+//     zero-fill kernels (rasterize_points.cu:120-128; 300 MB of memset at config 3) disappear;
+//   * SH rows (192 B in, 192 B out per Gaussian at degree 3) move through the TMA unit: cp.async.bulk
+//     global->shared for visible Gaussians only, cp.async.bulk shared->global for the gradient rows, staged in
+//     padded 208-byte shared-memory rows owned by one thread each (conflict-free 128-bit accesses, no
+//     block-level synchronisation besides the load mbarrier).
+#include "common.cuh"
+
+namespace gsr {
+
+namespace {
+
+constexpr int PB_THREADS = 128;
+constexpr int ROW_WORDS = 52;
+
+struct M3 {
+  float m[3][3];  // m[column][row]
+};
+__device__ __forceinline__ M3 mat_mul(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+  return R;
+}
+__device__ __forceinline__ M3 mat_t(const M3& A) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
+  return R;
+}
+
+struct PbArgs {
+  int P, D, M, W, H;
+  float tan_fovx, tan_fovy, h_x, h_y, scale_modifier;
+  const float* means3D;
+  const float* shs;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  const int32_t* radii;
+  const uint8_t* clamped;
+  const float* acc;
+  float* dL_dmeans3D;
+  float* dL_dmeans2D;
+  float* dL_dcolors;
+  float* dL_dopacity;
+  float* dL_dcov3D;
+  float* dL_dsh;
+  float* dL_dscales;
+  float* dL_drotations;
+};
+
+__device__ __forceinline__ M3 quat_to_R(float r, float x, float y, float z) {
+  M3 R;
+  R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
+  R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+  R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+  return R;
+}
+
+template <bool BULK>
+__global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs a) {
+  __shared__ __align__(16) float rows[BULK ? PB_THREADS * ROW_WORDS : 4];
+  __shared__ uint64_t bar;
+  const int idx = blockIdx.x * PB_THREADS + threadIdx.x;
+  const bool live = idx < a.P;
+  const bool vis = live && a.radii[idx] > 0;
+  const bool has_sh = a.shs != nullptr;
+  float* row = BULK ? &rows[threadIdx.x * ROW_WORDS] : nullptr;
+  const int nb = (a.D + 1) * (a.D + 1);  // active coefficients
+
+  if (BULK) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, PB_THREADS);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    const uint32_t nbytes = (uint32_t)((nb * 12 + 15) & ~15);
+    if (vis) {
+      mbar_arrive_expect_tx(&bar, nbytes);
+      bulk_g2s(row, a.shs + (size_t)idx * a.M * 3, nbytes, &bar);
+    } else {
+      mbar_arrive(&bar);
+    }
+  }
+
+  float dmean[3] = {0.f, 0.f, 0.f}, dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
+  float3 mean = make_float3(0.f, 0.f, 0.f);
+
+  if (vis) {
+    const float4* ap = reinterpret_cast<const float4*>(a.acc + (size_t)idx * ACC_STRIDE);
+    acc0 = __ldg(ap);      // dcolor.rgb, dmean2D.x
+    acc1 = __ldg(ap + 1);  // dmean2D.y, dconic.a, dconic.b, dconic.c
+    acc2 = __ldg(ap + 2);  // dopacity
+    mean = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+
+    // ---- 3-D covariance (recomputed; forward.cu:118-152) ----
+    float cov3D[6];
+    float3 sc = make_float3(0.f, 0.f, 0.f);
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    M3 R, Mm;
+    if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[(size_t)idx * 6 + k];
+    } else {
+      sc = make_float3(a.scale_modifier * a.scales[3 * idx], a.scale_modifier * a.scales[3 * idx + 1],
+                       a.scale_modifier * a.scales[3 * idx + 2]);
+      q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+      R = quat_to_R(q.x, q.y, q.z, q.w);
+      // M = S * R (GLM): M[c][r] = s_r * R[c][r]
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        Mm.m[c][0] = sc.x * R.m[c][0];
+        Mm.m[c][1] = sc.y * R.m[c][1];
+        Mm.m[c][2] = sc.z * R.m[c][2];
+      }
+      M3 Sigma = mat_mul(mat_t(Mm), Mm);
+      cov3D[0] = Sigma.m[0][0]; cov3D[1] = Sigma.m[0][1]; cov3D[2] = Sigma.m[0][2];
+      cov3D[3] = Sigma.m[1][1]; cov3D[4] = Sigma.m[1][2]; cov3D[5] = Sigma.m[2][2];
+    }
+
+    // ---- backward of the 2-D covariance / conic (backward.cu:164-273) ----
+    {
+      const float* vm = a.view;
+      float3 t;
+      t.x = vm[0] * mean.x + vm[4] * mean.y + vm[8] * mean.z + vm[12];
+      t.y = vm[1] * mean.x + vm[5] * mean.y + vm[9] * mean.z + vm[13];
+      t.z = vm[2] * mean.x + vm[6] * mean.y + vm[10] * mean.z + vm[14];
+      const float limx = 1.3f * a.tan_fovx, limy = 1.3f * a.tan_fovy;
+      const float txtz = t.x / t.z, tytz = t.y / t.z;
+      t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+      t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+      const float x_grad_mul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
+      const float y_grad_mul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
+      M3 J;
+      J.m[0][0] = a.h_x / t.z; J.m[0][1] = 0.f; J.m[0][2] = -(a.h_x * t.x) / (t.z * t.z);
+      J.m[1][0] = 0.f; J.m[1][1] = a.h_y / t.z; J.m[1][2] = -(a.h_y * t.y) / (t.z * t.z);
+      J.m[2][0] = 0.f; J.m[2][1] = 0.f; J.m[2][2] = 0.f;
+      M3 Wm;
+      Wm.m[0][0] = vm[0]; Wm.m[0][1] = vm[4]; Wm.m[0][2] = vm[8];
+      Wm.m[1][0] = vm[1]; Wm.m[1][1] = vm[5]; Wm.m[1][2] = vm[9];
+      Wm.m[2][0] = vm[2]; Wm.m[2][1] = vm[6]; Wm.m[2][2] = vm[10];
+      M3 Vrk;
+      Vrk.m[0][0] = cov3D[0]; Vrk.m[0][1] = cov3D[1]; Vrk.m[0][2] = cov3D[2];
+      Vrk.m[1][0] = cov3D[1]; Vrk.m[1][1] = cov3D[3]; Vrk.m[1][2] = cov3D[4];
+      Vrk.m[2][0] = cov3D[2]; Vrk.m[2][1] = cov3D[4]; Vrk.m[2][2] = cov3D[5];
+      const M3 T = mat_mul(Wm, J);
+      const M3 cov2D = mat_mul(mat_mul(mat_t(T), mat_t(Vrk)), T);
+      const float ca = cov2D.m[0][0] + 0.3f, cb = cov2D.m[0][1], cc = cov2D.m[1][1] + 0.3f;
+      const float gca = acc1.y, gcb = acc1.z, gcc = acc1.w;  // dL/dconic (a, b, c)
+      const float denom = ca * cc - cb * cb;
+      float dL_da = 0.f, dL_db = 0.f, dL_dc = 0.f;
+      const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+      if (denom2inv != 0.f) {
+        dL_da = denom2inv * (-cc * cc * gca + 2 * cb * cc * gcb + (denom - ca * cc) * gcc);
+        dL_dc = denom2inv * (-ca * ca * gcc + 2 * ca * cb * gcb + (denom - ca * cc) * gca);
+        dL_db = denom2inv * 2 * (cb * cc * gca - (denom + 2 * cb * cb) * gcb + ca * cb * gcc);
+        dcov[0] = (T.m[0][0] * T.m[0][0] * dL_da + T.m[0][0] * T.m[1][0] * dL_db + T.m[1][0] * T.m[1][0] * dL_dc);
+        dcov[3] = (T.m[0][1] * T.m[0][1] * dL_da + T.m[0][1] * T.m[1][1] * dL_db + T.m[1][1] * T.m[1][1] * dL_dc);
+        dcov[5] = (T.m[0][2] * T.m[0][2] * dL_da + T.m[0][2] * T.m[1][2] * dL_db + T.m[1][2] * T.m[1][2] * dL_dc);
+        dcov[1] = 2 * T.m[0][0] * T.m[0][1] * dL_da + (T.m[0][0] * T.m[1][1] + T.m[0][1] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][1] * dL_dc;
+        dcov[2] = 2 * T.m[0][0] * T.m[0][2] * dL_da + (T.m[0][0] * T.m[1][2] + T.m[0][2] * T.m[1][0]) * dL_db + 2 * T.m[1][0] * T.m[1][2] * dL_dc;
+        dcov[4] = 2 * T.m[0][2] * T.m[0][1] * dL_da + (T.m[0][1] * T.m[1][2] + T.m[0][2] * T.m[1][1]) * dL_db + 2 * T.m[1][1] * T.m[1][2] * dL_dc;
+      }
+      // u_i = row i of T against Vrk column j
+      float u0[3], u1[3];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        u0[j] = T.m[0][0] * Vrk.m[j][0] + T.m[0][1] * Vrk.m[j][1] + T.m[0][2] * Vrk.m[j][2];
+        u1[j] = T.m[1][0] * Vrk.m[j][0] + T.m[1][1] * Vrk.m[j][1] + T.m[1][2] * Vrk.m[j][2];
+      }
+      const float dL_dT00 = 2 * u0[0] * dL_da + u1[0] * dL_db;
+      const float dL_dT01 = 2 * u0[1] * dL_da + u1[1] * dL_db;
+      const float dL_dT02 = 2 * u0[2] * dL_da + u1[2] * dL_db;
+      const float dL_dT10 = 2 * u1[0] * dL_dc + u0[0] * dL_db;
+      const float dL_dT11 = 2 * u1[1] * dL_dc + u0[1] * dL_db;
+      const float dL_dT12 = 2 * u1[2] * dL_dc + u0[2] * dL_db;
+      const float dL_dJ00 = Wm.m[0][0] * dL_dT00 + Wm.m[0][1] * dL_dT01 + Wm.m[0][2] * dL_dT02;
+      const float dL_dJ02 = Wm.m[2][0] * dL_dT00 + Wm.m[2][1] * dL_dT01 + Wm.m[2][2] * dL_dT02;
+      const float dL_dJ11 = Wm.m[1][0] * dL_dT10 + Wm.m[1][1] * dL_dT11 + Wm.m[1][2] * dL_dT12;
+      const float dL_dJ12 = Wm.m[2][0] * dL_dT10 + Wm.m[2][1] * dL_dT11 + Wm.m[2][2] * dL_dT12;
+      const float tz = 1.f / t.z, tz2 = tz * tz, tz3 = tz2 * tz;
+      const float dL_dtx = x_grad_mul * -a.h_x * tz2 * dL_dJ02;
+      const float dL_dty = y_grad_mul * -a.h_y * tz2 * dL_dJ12;
+      const float dL_dtz = -a.h_x * tz2 * dL_dJ00 - a.h_y * tz2 * dL_dJ11 + (2 * a.h_x * t.x) * tz3 * dL_dJ02 +
+                           (2 * a.h_y * t.y) * tz3 * dL_dJ12;
+      // transformVec4x3Transpose (auxiliary.h:89-97)
+      dmean[0] = vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz;
+      dmean[1] = vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz;
+      dmean[2] = vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz;
+    }
+
+    // ---- projection term (backward.cu:372-387) ----
+    {
+      const float* proj = a.proj;
+      const float hw = proj[3] * mean.x + proj[7] * mean.y + proj[11] * mean.z + proj[15];
+      const float m_w = 1.0f / (hw + 0.0000001f);
+      const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+      const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+      const float g2x = acc0.w, g2y = acc1.x;
+      dmean[0] += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
+      dmean[1] += (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
+      dmean[2] += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
+    }
+
+    // ---- 3-D covariance -> scale / rotation (backward.cu:278-341) ----
+    if (a.cov3D_precomp == nullptr) {
+      M3 dSig;
+      dSig.m[0][0] = dcov[0]; dSig.m[0][1] = 0.5f * dcov[1]; dSig.m[0][2] = 0.5f * dcov[2];
+      dSig.m[1][0] = 0.5f * dcov[1]; dSig.m[1][1] = dcov[3]; dSig.m[1][2] = 0.5f * dcov[4];
+      dSig.m[2][0] = 0.5f * dcov[2]; dSig.m[2][1] = 0.5f * dcov[4]; dSig.m[2][2] = dcov[5];
+      M3 twoM;
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) twoM.m[c][r] = Mm.m[c][r] * 2.0f;
+      const M3 dL_dM = mat_mul(twoM, dSig);
+      const M3 Rt = mat_t(R);
+      M3 dMt = mat_t(dL_dM);
+      dscale[0] = Rt.m[0][0] * dMt.m[0][0] + Rt.m[0][1] * dMt.m[0][1] + Rt.m[0][2] * dMt.m[0][2];
+      dscale[1] = Rt.m[1][0] * dMt.m[1][0] + Rt.m[1][1] * dMt.m[1][1] + Rt.m[1][2] * dMt.m[1][2];
+      dscale[2] = Rt.m[2][0] * dMt.m[2][0] + Rt.m[2][1] * dMt.m[2][1] + Rt.m[2][2] * dMt.m[2][2];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        dMt.m[0][k] *= sc.x;
+        dMt.m[1][k] *= sc.y;
+        dMt.m[2][k] *= sc.z;
+      }
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      drot[0] = 2 * z * (dMt.m[0][1] - dMt.m[1][0]) + 2 * y * (dMt.m[2][0] - dMt.m[0][2]) + 2 * x * (dMt.m[1][2] - dMt.m[2][1]);
+      drot[1] = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
+      drot[2] = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
+      drot[3] = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+    }
+  }
+
+  // ---- SH backward (backward.cu:20-139) ----
+  if (BULK) mbar_wait(&bar, 0);
+  if (has_sh && live) {
+    float dsh[48];
+#pragma unroll
+    for (int i = 0; i < 48; i++) dsh[i] = 0.f;
+    if (vis) {
+      const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
+      const float C2_0 = 1.0925484305920792f, C2_1 = -1.0925484305920792f, C2_2 = 0.31539156525252005f,
+                  C2_3 = -1.0925484305920792f, C2_4 = 0.5462742152960396f;
+      const float C3_0 = -0.5900435899266435f, C3_1 = 2.890611442640554f, C3_2 = -0.4570457994644658f,
+                  C3_3 = 0.3731763325901154f, C3_4 = -0.4570457994644658f, C3_5 = 1.445305721320277f,
+                  C3_6 = -0.5900435899266435f;
+      float sh[48];
+      if (BULK) {
+        const int nvec = (nb * 3 + 3) >> 2;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (k < nvec) v4 = *reinterpret_cast<const float4*>(row + 4 * k);
+          sh[4 * k] = v4.x; sh[4 * k + 1] = v4.y; sh[4 * k + 2] = v4.z; sh[4 * k + 3] = v4.w;
+        }
+      } else {
+        const float* src = a.shs + (size_t)idx * a.M * 3;
+#pragma unroll
+        for (int i = 0; i < 48; i++) sh[i] = (i < nb * 3) ? src[i] : 0.f;
+      }
+      const float3 dir_orig = make_float3(mean.x - a.campos[0], mean.y - a.campos[1], mean.z - a.campos[2]);
+      const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+      const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+      const uint8_t cl = a.clamped[idx];
+      float dRGB[3] = {acc0.x * ((cl & 1) ? 0.f : 1.f), acc0.y * ((cl & 2) ? 0.f : 1.f), acc0.z * ((cl & 4) ? 0.f : 1.f)};
+      float bs[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) bs[i] = 0.f;
+      float ddir[3] = {0.f, 0.f, 0.f};
+      bs[0] = C0;
+      if (a.D > 0) {
+        bs[1] = -C1 * y; bs[2] = C1 * z; bs[3] = -C1 * x;
+        float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        if (a.D > 1) {
+          bs[4] = C2_0 * xy; bs[5] = C2_1 * yz; bs[6] = C2_2 * (2.f * zz - xx - yy); bs[7] = C2_3 * xz; bs[8] = C2_4 * (xx - yy);
+          if (a.D > 2) {
+            bs[9] = C3_0 * y * (3.f * xx - yy); bs[10] = C3_1 * xy * z; bs[11] = C3_2 * y * (4.f * zz - xx - yy);
+            bs[12] = C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); bs[13] = C3_4 * x * (4.f * zz - xx - yy);
+            bs[14] = C3_5 * z * (xx - yy); bs[15] = C3_6 * x * (xx - 3.f * yy);
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          auto S = [&](int k) { return sh[3 * k + ch]; };
+          float dX = -C1 * S(3), dY = -C1 * S(1), dZ = C1 * S(2);
+          if (a.D > 1) {
+            dX += C2_0 * y * S(4) + C2_2 * 2.f * -x * S(6) + C2_3 * z * S(7) + C2_4 * 2.f * x * S(8);
+            dY += C2_0 * x * S(4) + C2_1 * z * S(5) + C2_2 * 2.f * -y * S(6) + C2_4 * 2.f * -y * S(8);
+            dZ += C2_1 * y * S(5) + C2_2 * 2.f * 2.f * z * S(6) + C2_3 * x * S(7);
+            if (a.D > 2) {
+              dX += (C3_0 * S(9) * 3.f * 2.f * xy + C3_1 * S(10) * yz + C3_2 * S(11) * -2.f * xy + C3_3 * S(12) * -3.f * 2.f * xz +
+                     C3_4 * S(13) * (-3.f * xx + 4.f * zz - yy) + C3_5 * S(14) * 2.f * xz + C3_6 * S(15) * 3.f * (xx - yy));
+              dY += (C3_0 * S(9) * 3.f * (xx - yy) + C3_1 * S(10) * xz + C3_2 * S(11) * (-3.f * yy + 4.f * zz - xx) +
+                     C3_3 * S(12) * -3.f * 2.f * yz + C3_4 * S(13) * -2.f * xy + C3_5 * S(14) * -2.f * yz + C3_6 * S(15) * -3.f * 2.f * xy);
+              dZ += (C3_1 * S(10) * xy + C3_2 * S(11) * 4.f * 2.f * yz + C3_3 * S(12) * 3.f * (2.f * zz - xx - yy) +
+                     C3_4 * S(13) * 4.f * 2.f * xz + C3_5 * S(14) * (xx - yy));
+            }
+          }
+          ddir[0] += dX * dRGB[ch];
+          ddir[1] += dY * dRGB[ch];
+          ddir[2] += dZ * dRGB[ch];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        dsh[3 * k] = bs[k] * dRGB[0];
+        dsh[3 * k + 1] = bs[k] * dRGB[1];
+        dsh[3 * k + 2] = bs[k] * dRGB[2];
+      }
+      // dnormvdv (auxiliary.h:107-117)
+      const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
+      const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
+      dmean[0] += ((+sum2 - dir_orig.x * dir_orig.x) * ddir[0] - dir_orig.y * dir_orig.x * ddir[1] - dir_orig.z * dir_orig.x * ddir[2]) * invsum32;
+      dmean[1] += (-dir_orig.x * dir_orig.y * ddir[0] + (sum2 - dir_orig.y * dir_orig.y) * ddir[1] - dir_orig.z * dir_orig.y * ddir[2]) * invsum32;
+      dmean[2] += (-dir_orig.x * dir_orig.z * ddir[0] - dir_orig.y * dir_orig.z * ddir[1] + (sum2 - dir_orig.z * dir_orig.z) * ddir[2]) * invsum32;
+    }
+    // ---- write the dL/dSH row (all M coefficients; zeros above the active degree / for culled Gaussians) ----
+    float* gdst = a.dL_dsh + (size_t)idx * a.M * 3;
+    const int nw = a.M * 3;
+    if (BULK) {
+#pragma unroll
+      for (int k = 0; k < 12; k++)
+        if (4 * k < nw) *reinterpret_cast<float4*>(row + 4 * k) = make_float4(dsh[4 * k], dsh[4 * k + 1], dsh[4 * k + 2], dsh[4 * k + 3]);
+      fence_proxy_async_smem();
+      bulk_s2g(gdst, row, (uint32_t)(nw * 4));
+      bulk_commit();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 48; i++)
+        if (i < nw) gdst[i] = dsh[i];
+    }
+  }
+
+  if (live) {
+    a.dL_dmeans3D[3 * idx] = dmean[0]; a.dL_dmeans3D[3 * idx + 1] = dmean[1]; a.dL_dmeans3D[3 * idx + 2] = dmean[2];
+    a.dL_dmeans2D[3 * idx] = acc0.w; a.dL_dmeans2D[3 * idx + 1] = acc1.x; a.dL_dmeans2D[3 * idx + 2] = 0.f;
+    a.dL_dcolors[3 * idx] = acc0.x; a.dL_dcolors[3 * idx + 1] = acc0.y; a.dL_dcolors[3 * idx + 2] = acc0.z;
+    a.dL_dopacity[idx] = acc2.x;
+#pragma unroll
+    for (int k = 0; k < 6; k++) a.dL_dcov3D[(size_t)idx * 6 + k] = dcov[k];
+    a.dL_dscales[3 * idx] = dscale[0]; a.dL_dscales[3 * idx + 1] = dscale[1]; a.dL_dscales[3 * idx + 2] = dscale[2];
+    *(reinterpret_cast<float4*>(a.dL_drotations) + idx) = make_float4(drot[0], drot[1], drot[2], drot[3]);
+  }
+  if (BULK) bulk_wait_read0();  // the row must stay valid until the TMA store has read it
+}
+
+}  // namespace
+
+int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
+                          const float* acc, const gsr_grads& gr, cudaStream_t st) {
+  PbArgs a;
+  a.P = c.P; a.D = s.sh_degree; a.M = s.sh_coeffs; a.W = s.image_width; a.H = s.image_height;
+  a.tan_fovx = s.tanfovx; a.tan_fovy = s.tanfovy;
+  a.h_y = a.H / (2.0f * s.tanfovy);
+  a.h_x = a.W / (2.0f * s.tanfovx);
+  a.scale_modifier = s.scale_modifier;
+  a.means3D = c.means3D; a.shs = c.shs; a.scales = c.scales; a.rotations = c.rotations;
+  a.cov3D_precomp = c.cov3D_precomp; a.view = s.viewmatrix; a.proj = s.projmatrix; a.campos = s.campos;
+  a.radii = radii; a.clamped = g.clamped; a.acc = acc;
+  a.dL_dmeans3D = gr.dL_dmeans3D; a.dL_dmeans2D = gr.dL_dmeans2D; a.dL_dcolors = gr.dL_dcolors;
+  a.dL_dopacity = gr.dL_dopacity; a.dL_dcov3D = gr.dL_dcov3D; a.dL_dsh = gr.dL_dsh;
+  a.dL_dscales = gr.dL_dscales; a.dL_drotations = gr.dL_drotations;
+  const int grid = (c.P + PB_THREADS - 1) / PB_THREADS;
+  const bool bulk = g_opt.preprocess_variant >= 1 && c.shs != nullptr && gr.dL_dsh != nullptr &&
+                    (s.sh_coeffs * 12) % 16 == 0 && s.sh_coeffs * 12 <= 192 &&
+                    (reinterpret_cast<uintptr_t>(c.shs) % 16) == 0 && (reinterpret_cast<uintptr_t>(gr.dL_dsh) % 16) == 0;
+  if (bulk)
+    preprocess_bwd_kernel<true><<<grid, PB_THREADS, 0, st>>>(a);
+  else
+    preprocess_bwd_kernel<false><<<grid, PB_THREADS, 0, st>>>(a);
+  g_launches++;
+  return check_launch("preprocess_bwd", s.debug != 0, st);
+}
+
+}  // namespace gsr

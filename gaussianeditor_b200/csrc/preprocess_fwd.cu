@@ -1,0 +1,335 @@
+// Forward per-Gaussian preprocess for sm_100a: near cull, projection, 3-D covariance, EWA 2-D covariance,
+// conic, screen radius, tile rectangle, SH -> RGB; writes one 48-byte splat record per visible Gaussian.
+//
+// Semantics follow the reference kernel preprocessCUDA (cuda_rasterizer/forward.cu:155-256 with its helpers
+// computeCov3D :118-152, computeCov2D :74-113, computeColorFromSH :20-71, and auxiliary.h:41-56,139-164).
+// The integer outputs (radii, tile counts) are discontinuous functions of the float chain, so the chain is
+// written with the SAME expression trees (GLM's column-major mat3 product order, type_mat3x3.inl:486-518;
+// ndc2Pix in fp64) and the default -fmad contraction, and is checked bit-for-bit against the reference's own
+// CUDA build on the B200 (tests/test_vs_reference_cuda.py).
+//
+// B200-specific structure:
+//   * the 192-byte SH row of each Gaussian that survives the near-plane test is fetched by the TMA unit
+//     (cp.async.bulk, one 16-byte-aligned row per thread, completion on one CTA mbarrier) into a padded
+//     shared-memory row while the thread does the covariance math; culled Gaussians (39 % of config 3)
+//     never touch their SH bytes. Rows are padded to 208 B so the 128-bit row reads are bank-conflict free.
+//   * outputs are packed AoS (SplatRecord) so the render kernels gather three float4 per splat.
+#include "common.cuh"
+
+namespace gsr {
+
+namespace {
+
+constexpr int PRE_THREADS = 128;
+constexpr int SH_ROW_WORDS = 52;  // 48 payload + 4 pad words: 208-byte rows
+
+struct M3 {
+  float m[3][3];  // m[column][row], GLM convention
+};
+
+// GLM's mat3 * mat3 (type_mat3x3.inl:486-518): Result[c][r] = A[0][r]*B[c][0] + A[1][r]*B[c][1] + A[2][r]*B[c][2]
+__device__ __forceinline__ M3 mat_mul(const M3& A, const M3& B) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
+  return R;
+}
+__device__ __forceinline__ M3 mat_t(const M3& A) {
+  M3 R;
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
+  return R;
+}
+
+__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+struct PreArgs {
+  int P, D, M, W, H, gx, gy;
+  float tan_fovx, tan_fovy, focal_x, focal_y, scale_modifier;
+  const float* means3D;
+  const float* opacities;
+  const float* shs;
+  const float* colors_precomp;
+  const float* scales;
+  const float* rotations;
+  const float* cov3D_precomp;
+  const float* view;
+  const float* proj;
+  const float* campos;
+  SplatRecord* records;
+  uint32_t* tiles_touched;
+  uint8_t* clamped;
+  uint32_t* depth_keys;
+  uint32_t* ident;
+  int32_t* radii;
+};
+
+// SH basis-weighted sum, one colour channel; `sh(k)` yields coefficient k of this channel.
+// Order of operations as forward.cu:30-61.
+template <typename ShFn>
+__device__ __forceinline__ float sh_channel(int deg, float x, float y, float z, ShFn sh) {
+  const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
+  const float C2_0 = 1.0925484305920792f, C2_1 = -1.0925484305920792f, C2_2 = 0.31539156525252005f,
+              C2_3 = -1.0925484305920792f, C2_4 = 0.5462742152960396f;
+  const float C3_0 = -0.5900435899266435f, C3_1 = 2.890611442640554f, C3_2 = -0.4570457994644658f,
+              C3_3 = 0.3731763325901154f, C3_4 = -0.4570457994644658f, C3_5 = 1.445305721320277f,
+              C3_6 = -0.5900435899266435f;
+  float result = C0 * sh(0);
+  if (deg > 0) {
+    result = result - C1 * y * sh(1) + C1 * z * sh(2) - C1 * x * sh(3);
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z;
+      float xy = x * y, yz = y * z, xz = x * z;
+      result = result + C2_0 * xy * sh(4) + C2_1 * yz * sh(5) + C2_2 * (2.0f * zz - xx - yy) * sh(6) +
+               C2_3 * xz * sh(7) + C2_4 * (xx - yy) * sh(8);
+      if (deg > 2) {
+        result = result + C3_0 * y * (3.0f * xx - yy) * sh(9) + C3_1 * xy * z * sh(10) +
+                 C3_2 * y * (4.0f * zz - xx - yy) * sh(11) + C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh(12) +
+                 C3_4 * x * (4.0f * zz - xx - yy) * sh(13) + C3_5 * z * (xx - yy) * sh(14) +
+                 C3_6 * x * (xx - 3.0f * yy) * sh(15);
+      }
+    }
+  }
+  return result + 0.5f;
+}
+
+template <bool BULK_SH>
+__global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreArgs a) {
+  __shared__ __align__(16) float sh_rows[BULK_SH ? PRE_THREADS * SH_ROW_WORDS : 4];
+  __shared__ uint64_t bar;
+
+  const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+  const bool live = idx < a.P;
+
+  if (BULK_SH) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, PRE_THREADS);
+      fence_mbar_init();
+    }
+    __syncthreads();
+  }
+
+  // ---- near cull (auxiliary.h:139-164; only the view-space z test is active) ----
+  float3 p_orig = make_float3(0.f, 0.f, 0.f);
+  float3 p_view = make_float3(0.f, 0.f, 0.f);
+  bool vis = false;
+  if (live) {
+    p_orig = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    const float* m = a.view;
+    p_view.x = m[0] * p_orig.x + m[4] * p_orig.y + m[8] * p_orig.z + m[12];
+    p_view.y = m[1] * p_orig.x + m[5] * p_orig.y + m[9] * p_orig.z + m[13];
+    p_view.z = m[2] * p_orig.x + m[6] * p_orig.y + m[10] * p_orig.z + m[14];
+    vis = !(p_view.z <= 0.2f);
+  }
+  const bool want_sh = a.colors_precomp == nullptr;
+  if (BULK_SH) {
+    // One TMA row fetch per surviving Gaussian; everybody arrives exactly once on the CTA barrier.
+    const uint32_t nbytes = (uint32_t)(((a.D + 1) * (a.D + 1) * 12 + 15) & ~15);
+    if (vis && want_sh) {
+      mbar_arrive_expect_tx(&bar, nbytes);
+      bulk_g2s(&sh_rows[threadIdx.x * SH_ROW_WORDS], a.shs + (size_t)idx * a.M * 3, nbytes, &bar);
+    } else {
+      mbar_arrive(&bar);
+    }
+  }
+
+  int my_radius_i = 0;
+  uint32_t tiles = 0;
+  uint32_t depth_key = 0xFFFFFFFFu;
+  SplatRecord rec;
+  bool emit = false;
+
+  if (vis) {
+    // ---- projection (forward.cu:196-200) ----
+    const float* pm = a.proj;
+    float4 p_hom;
+    p_hom.x = pm[0] * p_orig.x + pm[4] * p_orig.y + pm[8] * p_orig.z + pm[12];
+    p_hom.y = pm[1] * p_orig.x + pm[5] * p_orig.y + pm[9] * p_orig.z + pm[13];
+    p_hom.z = pm[2] * p_orig.x + pm[6] * p_orig.y + pm[10] * p_orig.z + pm[14];
+    p_hom.w = pm[3] * p_orig.x + pm[7] * p_orig.y + pm[11] * p_orig.z + pm[15];
+    float p_w = 1.0f / (p_hom.w + 0.0000001f);
+    float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+
+    // ---- 3-D covariance (forward.cu:118-152); the quaternion is used as given ----
+    float cov3D[6];
+    if (a.cov3D_precomp != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[(size_t)idx * 6 + k];
+    } else {
+      const float3 scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+      const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+      M3 S;
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) S.m[c][r] = (c == r) ? 1.0f : 0.0f;
+      S.m[0][0] = a.scale_modifier * scale.x;
+      S.m[1][1] = a.scale_modifier * scale.y;
+      S.m[2][2] = a.scale_modifier * scale.z;
+      float r = q.x, x = q.y, y = q.z, z = q.w;
+      M3 R;
+      R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
+      R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
+      R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
+      M3 Mm = mat_mul(S, R);
+      M3 Sigma = mat_mul(mat_t(Mm), Mm);
+      cov3D[0] = Sigma.m[0][0]; cov3D[1] = Sigma.m[0][1]; cov3D[2] = Sigma.m[0][2];
+      cov3D[3] = Sigma.m[1][1]; cov3D[4] = Sigma.m[1][2]; cov3D[5] = Sigma.m[2][2];
+    }
+
+    // ---- EWA 2-D covariance (forward.cu:74-113) ----
+    float3 t = p_view;  // transformPoint4x3(mean, viewmatrix) again in the reference; same value
+    const float limx = 1.3f * a.tan_fovx;
+    const float limy = 1.3f * a.tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
+    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
+    M3 J;
+    J.m[0][0] = a.focal_x / t.z; J.m[0][1] = 0.0f; J.m[0][2] = -(a.focal_x * t.x) / (t.z * t.z);
+    J.m[1][0] = 0.0f; J.m[1][1] = a.focal_y / t.z; J.m[1][2] = -(a.focal_y * t.y) / (t.z * t.z);
+    J.m[2][0] = 0.0f; J.m[2][1] = 0.0f; J.m[2][2] = 0.0f;
+    const float* vm = a.view;
+    M3 Wm;
+    Wm.m[0][0] = vm[0]; Wm.m[0][1] = vm[4]; Wm.m[0][2] = vm[8];
+    Wm.m[1][0] = vm[1]; Wm.m[1][1] = vm[5]; Wm.m[1][2] = vm[9];
+    Wm.m[2][0] = vm[2]; Wm.m[2][1] = vm[6]; Wm.m[2][2] = vm[10];
+    M3 T = mat_mul(Wm, J);
+    M3 Vrk;
+    Vrk.m[0][0] = cov3D[0]; Vrk.m[0][1] = cov3D[1]; Vrk.m[0][2] = cov3D[2];
+    Vrk.m[1][0] = cov3D[1]; Vrk.m[1][1] = cov3D[3]; Vrk.m[1][2] = cov3D[4];
+    Vrk.m[2][0] = cov3D[2]; Vrk.m[2][1] = cov3D[4]; Vrk.m[2][2] = cov3D[5];
+    M3 cov = mat_mul(mat_mul(mat_t(T), mat_t(Vrk)), T);
+    cov.m[0][0] += 0.3f;
+    cov.m[1][1] += 0.3f;
+    const float3 cov2 = make_float3(cov.m[0][0], cov.m[0][1], cov.m[1][1]);
+
+    // ---- conic, radius, tile rectangle (forward.cu:218-237, auxiliary.h:46-56) ----
+    float det = (cov2.x * cov2.z - cov2.y * cov2.y);
+    if (det != 0.0f) {
+      float det_inv = 1.f / det;
+      float3 conic = make_float3(cov2.z * det_inv, -cov2.y * det_inv, cov2.x * det_inv);
+      float mid = 0.5f * (cov2.x + cov2.z);
+      float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
+      float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
+      float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+      float2 point_image = make_float2(ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H));
+      const int max_radius = (int)my_radius;
+      uint2 rect_min, rect_max;
+      rect_min.x = (unsigned)min(a.gx, max((int)0, (int)((point_image.x - max_radius) / TILE)));
+      rect_min.y = (unsigned)min(a.gy, max((int)0, (int)((point_image.y - max_radius) / TILE)));
+      rect_max.x = (unsigned)min(a.gx, max((int)0, (int)((point_image.x + max_radius + TILE - 1) / TILE)));
+      rect_max.y = (unsigned)min(a.gy, max((int)0, (int)((point_image.y + max_radius + TILE - 1) / TILE)));
+      tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+      if (tiles != 0) {
+        emit = true;
+        my_radius_i = max_radius;
+        depth_key = __float_as_uint(p_view.z);
+        rec.q0 = make_float4(point_image.x, point_image.y, conic.x, conic.y);
+        rec.q1 = make_float4(conic.z, a.opacities[idx], p_view.z, 0.f);
+      }
+    }
+  }
+
+  // ---- colour (forward.cu:20-71) ----
+  uint8_t clamp_bits = 0;
+  if (BULK_SH) mbar_wait(&bar, 0);  // all rows of this CTA have landed (every thread waits: no divergent exit before)
+  if (emit) {
+    float3 rgb;
+    if (!want_sh) {
+      rgb = make_float3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
+    } else {
+      float3 dir = make_float3(p_orig.x - a.campos[0], p_orig.y - a.campos[1], p_orig.z - a.campos[2]);
+      float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+      dir.x = dir.x / len;
+      dir.y = dir.y / len;
+      dir.z = dir.z / len;
+      float res[3];
+      if (BULK_SH) {
+        const float* row = &sh_rows[threadIdx.x * SH_ROW_WORDS];
+        // pull the row into registers with 128-bit shared loads (row stride 208 B: conflict-free)
+        float v[48];
+        const int nvec = ((a.D + 1) * (a.D + 1) * 3 + 3) >> 2;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+          if (k < nvec) {
+            float4 q = *reinterpret_cast<const float4*>(row + 4 * k);
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+          } else {
+            v[4 * k] = v[4 * k + 1] = v[4 * k + 2] = v[4 * k + 3] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) res[ch] = sh_channel(a.D, dir.x, dir.y, dir.z, [&](int k) { return v[3 * k + ch]; });
+      } else {
+        const float* sh = a.shs + (size_t)idx * a.M * 3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) res[ch] = sh_channel(a.D, dir.x, dir.y, dir.z, [&](int k) { return sh[3 * k + ch]; });
+      }
+      clamp_bits = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
+      rgb = make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
+    }
+    rec.q2 = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+    float4* dst = reinterpret_cast<float4*>(a.records + idx);
+    dst[0] = rec.q0;
+    dst[1] = rec.q1;
+    dst[2] = rec.q2;
+  }
+  if (live) {
+    a.radii[idx] = my_radius_i;
+    a.tiles_touched[idx] = tiles;
+    a.clamped[idx] = clamp_bits;
+    a.depth_keys[idx] = depth_key;
+    a.ident[idx] = (uint32_t)idx;
+  }
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  float x = means3D[3 * idx], y = means3D[3 * idx + 1], z = means3D[3 * idx + 2];
+  float vz = view[2] * x + view[6] * y + view[10] * z + view[14];
+  present[idx] = !(vz <= 0.2f);
+}
+
+}  // namespace
+
+int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
+                          cudaStream_t st) {
+  PreArgs a;
+  a.P = c.P; a.D = s.sh_degree; a.M = s.sh_coeffs; a.W = s.image_width; a.H = s.image_height;
+  a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
+  a.tan_fovx = s.tanfovx; a.tan_fovy = s.tanfovy;
+  a.focal_y = a.H / (2.0f * s.tanfovy);  // rasterizer_impl.cu:190-191
+  a.focal_x = a.W / (2.0f * s.tanfovx);
+  a.scale_modifier = s.scale_modifier;
+  a.means3D = c.means3D; a.opacities = c.opacities; a.shs = c.shs; a.colors_precomp = c.colors_precomp;
+  a.scales = c.scales; a.rotations = c.rotations; a.cov3D_precomp = c.cov3D_precomp;
+  a.view = s.viewmatrix; a.proj = s.projmatrix; a.campos = s.campos;
+  a.records = g.records; a.tiles_touched = g.tiles_touched; a.clamped = g.clamped;
+  a.depth_keys = g.depth_keys; a.ident = g.ident; a.radii = radii;
+  const int grid = (c.P + PRE_THREADS - 1) / PRE_THREADS;
+  // TMA row fetch needs 16-byte aligned rows: M*12 % 16 == 0 and an aligned base pointer.
+  const bool bulk = g_opt.preprocess_variant >= 1 && c.colors_precomp == nullptr && c.shs != nullptr &&
+                    (s.sh_coeffs * 12) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.shs) % 16) == 0 &&
+                    (s.sh_coeffs * 12) <= 192;
+  if (bulk)
+    preprocess_fwd_kernel<true><<<grid, PRE_THREADS, 0, st>>>(a);
+  else
+    preprocess_fwd_kernel<false><<<grid, PRE_THREADS, 0, st>>>(a);
+  g_launches++;
+  return check_launch("preprocess_fwd", s.debug != 0, st);
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st) {
+  mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, viewmatrix, present);
+  g_launches++;
+  return check_launch("mark_visible", false, st);
+}
+
+}  // namespace gsr

@@ -1,0 +1,364 @@
+// Backward of the alpha blending for sm_100a: per-pixel dL/dcolor -> per-Gaussian 2-D gradients
+// (dL/dcolor, dL/dmean2D, dL/dconic, dL/dopacity), accumulated into the 48-byte-per-Gaussian scratch `acc`.
+//
+// Semantics: renderCUDA (bwd) of the reference (cuda_rasterizer/backward.cu:399-557): walk each tile's list
+// back to front, skip list positions behind the pixel's last contributor, recompute G = exp(power) and alpha
+// with the forward's arithmetic (same skip decisions), T <- T/(1-alpha), and accumulate nine partial sums per
+// (pixel, splat) hit.
+//
+// The reference issues nine global float atomics PER HIT (~10^9 REDG at config 3) and walks every tile list
+// from its very end.  Here:
+//   * the walk starts at tile_last = max n_contrib of the tile (written by the forward): on a saturated scene
+//     three quarters of every list lie behind the last contributor of all 256 pixels and are never loaded;
+//   * variant 1 (default): one warp owns a whole tile (or half of it), each lane owns one pixel of each of its
+//     8x4 sub-blocks; the nine partial sums are first accumulated over the lane's own pixels in registers,
+//     then summed across the warp with a transposing butterfly (14 shuffles for 9 values instead of 45), and
+//     only then added to global memory: 9 atomics per (tile, splat) instead of 9 per (pixel, splat);
+//   * the same opacity-aware sub-block culling as the forward (render_fwd.cu) removes splats whose
+//     alpha>=1/255 ellipse misses the sub-block before any pixel looks at them.
+// Variant 0: the reference's CTA-per-tile structure with a plain warp-shuffle reduction before the atomics.
+//
+// Gradients are sums of floats in a different order than the reference's atomics (which are themselves
+// non-deterministic), so parity is to tolerance (tests: rel L2 <= 1e-4), not bit-exact.
+#include "common.cuh"
+
+namespace gsr {
+
+namespace {
+
+struct BwdArgs {
+  const uint2* ranges;
+  const uint32_t* point_list;
+  const SplatRecord* records;
+  const uint32_t* tile_last;
+  int W, H, gx, gy;
+  const float* bg;
+  const float* final_T;
+  const uint32_t* n_contrib;
+  const float* dL_dpix;
+  float* acc;  // [P, ACC_STRIDE]
+};
+
+// One (pixel, splat) hit. `ar*` is the reference's accum_rec updated eagerly (same operands, same order as
+// backward.cu:515), `bgT` = T_final * (bg . dL_dpixel).
+struct PixState {
+  float T, ar0, ar1, ar2, d0, d1, d2, bgT;
+};
+
+__device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, float dy, float G, float alpha, float A,
+                                           float B, float C, float o, float c0, float c1, float c2, float ddelx_dx,
+                                           float ddely_dy) {
+  const float oma = 1.f - alpha;
+  const float rcp = 1.f / oma;
+  p.T = p.T * rcp;
+  const float dchannel_dcolor = alpha * p.T;
+  float dL_dalpha = (c0 - p.ar0) * p.d0;
+  dL_dalpha = fmaf(c1 - p.ar1, p.d1, dL_dalpha);
+  dL_dalpha = fmaf(c2 - p.ar2, p.d2, dL_dalpha);
+  g[0] = fmaf(dchannel_dcolor, p.d0, g[0]);
+  g[1] = fmaf(dchannel_dcolor, p.d1, g[1]);
+  g[2] = fmaf(dchannel_dcolor, p.d2, g[2]);
+  p.ar0 = fmaf(alpha, c0, oma * p.ar0);
+  p.ar1 = fmaf(alpha, c1, oma * p.ar1);
+  p.ar2 = fmaf(alpha, c2, oma * p.ar2);
+  dL_dalpha = fmaf(dL_dalpha, p.T, -p.bgT * rcp);
+  const float dL_dG = o * dL_dalpha;
+  const float gdx = G * dx, gdy = G * dy;
+  const float dG_ddelx = -gdx * A - gdy * B;
+  const float dG_ddely = -gdy * C - gdx * B;
+  g[3] = fmaf(dL_dG * dG_ddelx, ddelx_dx, g[3]);
+  g[4] = fmaf(dL_dG * dG_ddely, ddely_dy, g[4]);
+  g[5] = fmaf(-0.5f * gdx * dx, dL_dG, g[5]);
+  g[6] = fmaf(-0.5f * gdx * dy, dL_dG, g[6]);
+  g[7] = fmaf(-0.5f * gdy * dy, dL_dG, g[7]);
+  g[8] = fmaf(G, dL_dalpha, g[8]);
+}
+
+// Sum nine per-lane values over the warp. g[0..7] go through a transposing butterfly: after it, lane 4*j (and
+// its three neighbours) holds the warp total of g[j]; g[8] takes a plain butterfly. Returns this lane's total of
+// value (lane>>2), and the total of g[8] in `g8`.
+__device__ __forceinline__ float warp_sum9(const float* g, int lane, float& g8) {
+  const unsigned F = 0xffffffffu;
+  float a[4], b[2], c;
+  {
+    const bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const float keep = up ? g[4 + i] : g[i];
+      const float send = up ? g[i] : g[4 + i];
+      a[i] = keep + __shfl_xor_sync(F, send, 16);
+    }
+  }
+  {
+    const bool up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const float keep = up ? a[2 + i] : a[i];
+      const float send = up ? a[i] : a[2 + i];
+      b[i] = keep + __shfl_xor_sync(F, send, 8);
+    }
+  }
+  {
+    const bool up = lane & 4;
+    const float keep = up ? b[1] : b[0];
+    const float send = up ? b[0] : b[1];
+    c = keep + __shfl_xor_sync(F, send, 4);
+  }
+  c += __shfl_xor_sync(F, c, 2);
+  c += __shfl_xor_sync(F, c, 1);
+  float t = g[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(F, t, o);
+  g8 = t;
+  return c;
+}
+
+// Same test as the forward's (render_fwd.cu); duplicated so each translation unit stays self-contained.
+__device__ __forceinline__ uint32_t subblock_mask_bwd(const float4 q0, const float4 q1, float X0, float Y0) {
+  const float A = q0.z, B = q0.w, C = q1.x, o = q1.y;
+  if (o < 1.0f / 255.0f) return 0u;
+  const float det = A * C - B * B;
+  if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f)) return 0xFFu;
+  const float tau2 = 2.0f * (__logf(o * 255.0f) * 1.001f + 1e-3f);
+  const float inv = tau2 / det;
+  const float ex = sqrtf(inv * C) * 1.001f + 0.02f;
+  const float ey = sqrtf(inv * A) * 1.001f + 0.02f;
+  if (!(ex < 1e30f) || !(ey < 1e30f)) return 0xFFu;
+  const float xlo = q0.x - ex - X0, xhi = q0.x + ex - X0;
+  const float ylo = q0.y - ey - Y0, yhi = q0.y + ey - Y0;
+  uint32_t cols = 0, rows = 0;
+  if (xhi >= 0.f && xlo <= 7.f) cols |= 0x55u;
+  if (xhi >= 8.f && xlo <= 15.f) cols |= 0xAAu;
+  if (yhi >= 0.f && ylo <= 3.f) rows |= 0x03u;
+  if (yhi >= 4.f && ylo <= 7.f) rows |= 0x0Cu;
+  if (yhi >= 8.f && ylo <= 11.f) rows |= 0x30u;
+  if (yhi >= 12.f && ylo <= 15.f) rows |= 0xC0u;
+  return cols & rows;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Variant 1: NSB sub-blocks per warp (8 = one warp per tile, 4 = two warps per tile)
+// ------------------------------------------------------------------------------------------------------
+constexpr int BW_WARPS = 4;
+
+template <int NSB>
+__global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const BwdArgs a, const int ntiles) {
+  __shared__ float4 s_stage[BW_WARPS][3][32];
+  __shared__ uint32_t s_id[BW_WARPS][32];
+  constexpr int PARTS = 8 / NSB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * BW_WARPS + warp;
+  const int tile = gw / PARTS, part = gw % PARTS;
+  if (tile >= ntiles) return;
+  float4(*stg)[32] = s_stage[warp];
+  uint32_t* sid = s_id[warp];
+
+  const int tx = tile % a.gx, ty = tile / a.gx;
+  const int lx = lane & 7, ly = lane >> 3;
+  const float X0 = (float)(tx * TILE), Y0 = (float)(ty * TILE);
+  const float fx = X0 + (float)lx, fy = Y0 + (float)ly;
+  const uint2 range = a.ranges[tile];
+  if (a.tile_last[tile] == 0) return;
+  const size_t HW = (size_t)a.H * a.W;
+  const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
+  const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+
+  PixState ps[NSB];
+  uint32_t nc[NSB], sblast[NSB];
+  uint32_t my_last = 0;
+#pragma unroll
+  for (int k = 0; k < NSB; k++) {
+    const int kg = part * NSB + k;
+    const int px = tx * TILE + 8 * (kg & 1) + lx, py = ty * TILE + 4 * (kg >> 1) + ly;
+    PixState p;
+    p.T = 0.f; p.ar0 = p.ar1 = p.ar2 = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
+    nc[k] = 0;
+    if (px < a.W && py < a.H) {
+      const size_t pix_id = (size_t)a.W * py + px;
+      const float Tf = a.final_T[pix_id];
+      p.T = Tf;
+      p.d0 = a.dL_dpix[pix_id];
+      p.d1 = a.dL_dpix[HW + pix_id];
+      p.d2 = a.dL_dpix[2 * HW + pix_id];
+      p.bgT = Tf * (bg0 * p.d0 + bg1 * p.d1 + bg2 * p.d2);
+      nc[k] = a.n_contrib[pix_id];
+    }
+    ps[k] = p;
+    sblast[k] = __reduce_max_sync(0xffffffffu, nc[k]);
+    my_last = max(my_last, sblast[k]);
+  }
+
+  for (int hi = (int)my_last; hi > 0; hi -= 32) {
+    // ---- stage positions hi, hi-1, ... (1-based), cull, compact (descending order is preserved) ----
+    const int pos = hi - lane;
+    uint32_t mask = 0, id = 0;
+    float4 q0, q1, q2;
+    if (pos >= 1) {
+      id = a.point_list[range.x + pos - 1];
+      const float4* r = reinterpret_cast<const float4*>(a.records + id);
+      q0 = __ldg(r);
+      q1 = __ldg(r + 1);
+      q2 = __ldg(r + 2);
+      mask = (subblock_mask_bwd(q0, q1, X0, Y0) >> (part * NSB)) & ((1u << NSB) - 1u);
+    }
+    const uint32_t keep = __ballot_sync(0xffffffffu, mask != 0);
+    const int cnt = __popc(keep);
+    if (mask != 0) {
+      const int slot = __popc(keep & ((1u << lane) - 1u));
+      q1.w = __uint_as_float(mask);
+      q2.w = __uint_as_float((uint32_t)pos);
+      stg[0][slot] = q0;
+      stg[1][slot] = q1;
+      stg[2][slot] = q2;
+      sid[slot] = id;
+    }
+    __syncwarp();
+    const uint32_t lo = (uint32_t)max(hi - 31, 1);
+    uint32_t act = 0;  // sub-blocks that can still have a contributor at these positions
+#pragma unroll
+    for (int k = 0; k < NSB; k++)
+      if (sblast[k] >= lo) act |= 1u << k;
+
+    for (int j = 0; j < cnt; j++) {
+      const float4 s1 = stg[1][j];
+      const uint32_t m = __float_as_uint(s1.w) & act;
+      if (m == 0) continue;
+      const float4 s0 = stg[0][j];
+      const float4 s2 = stg[2][j];
+      const uint32_t spos = __float_as_uint(s2.w);
+      float dxv[2], dxA[2], dxB[2], dyv[NSB / 2], t0[NSB / 2];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        dxv[c] = s0.x - (fx + 8.0f * c);
+        dxA[c] = __fmul_rn(dxv[c], s0.z);
+        dxB[c] = __fmul_rn(dxv[c], s0.w);
+      }
+#pragma unroll
+      for (int r = 0; r < NSB / 2; r++) {
+        dyv[r] = s0.y - (fy + 4.0f * (float)(part * (NSB / 2) + r));
+        t0[r] = __fmul_rn(__fmul_rn(dyv[r], s1.x), dyv[r]);
+      }
+      float g[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) g[i] = 0.f;
+      bool any = false;
+#pragma unroll
+      for (int k = 0; k < NSB; k++) {
+        if (!((m >> k) & 1u)) continue;  // warp-uniform
+        const int c = k & 1, r = k >> 1;  // NSB is even, so the column parity of sub-block part*NSB+k is k&1
+        const float dx = dxv[c], dy = dyv[r];
+        const float s = __fmaf_rn(dx, dxA[c], t0[r]);
+        const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(dxB[c], dy));
+        if (power > 0.0f || spos > nc[k]) continue;
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, __fmul_rn(s1.y, G));
+        if (alpha < 1.0f / 255.0f) continue;
+        any = true;
+        hit_update(ps[k], g, dx, dy, G, alpha, s0.z, s0.w, s1.x, s1.y, s2.x, s2.y, s2.z, ddelx_dx, ddely_dy);
+      }
+      if (__any_sync(0xffffffffu, any)) {
+        float g8;
+        const float tot = warp_sum9(g, lane, g8);
+        float* dst = a.acc + (size_t)sid[j] * ACC_STRIDE;
+        if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), tot);
+        if (lane == 1) atomicAdd(dst + 8, g8);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Variant 0: CTA per tile, one pixel per thread, butterfly reduction of the nine sums per splat
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs a) {
+  __shared__ float4 s_q0[TILE_PIX], s_q1[TILE_PIX], s_q2[TILE_PIX];
+  __shared__ uint32_t s_ids[TILE_PIX];
+  const int tile = blockIdx.y * a.gx + blockIdx.x;
+  const int tid = threadIdx.y * TILE + threadIdx.x;
+  const int lane = tid & 31;
+  const uint2 pix = make_uint2(blockIdx.x * TILE + threadIdx.x, blockIdx.y * TILE + threadIdx.y);
+  const bool inside = pix.x < (unsigned)a.W && pix.y < (unsigned)a.H;
+  const size_t pix_id = (size_t)a.W * pix.y + pix.x;
+  const float2 pixf = make_float2((float)pix.x, (float)pix.y);
+  const uint2 range = a.ranges[tile];
+  const int tl = (int)a.tile_last[tile];  // block-uniform
+  const size_t HW = (size_t)a.H * a.W;
+
+  PixState p;
+  p.T = 0.f; p.ar0 = p.ar1 = p.ar2 = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
+  uint32_t nc = 0;
+  if (inside) {
+    const float Tf = a.final_T[pix_id];
+    p.T = Tf;
+    p.d0 = a.dL_dpix[pix_id]; p.d1 = a.dL_dpix[HW + pix_id]; p.d2 = a.dL_dpix[2 * HW + pix_id];
+    p.bgT = Tf * (a.bg[0] * p.d0 + a.bg[1] * p.d1 + a.bg[2] * p.d2);
+    nc = a.n_contrib[pix_id];
+  }
+  const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+
+  for (int hi = tl; hi > 0; hi -= TILE_PIX) {
+    __syncthreads();
+    const int pos = hi - tid;
+    if (pos >= 1) {
+      const uint32_t id = a.point_list[range.x + pos - 1];
+      const float4* r = reinterpret_cast<const float4*>(a.records + id);
+      s_q0[tid] = __ldg(r); s_q1[tid] = __ldg(r + 1); s_q2[tid] = __ldg(r + 2);
+      s_ids[tid] = id;
+    }
+    __syncthreads();
+    const int n = min(TILE_PIX, hi);
+    for (int j = 0; j < n; j++) {
+      const uint32_t spos = (uint32_t)(hi - j);
+      const float4 q0 = s_q0[j], q1 = s_q1[j];
+      const float dx = q0.x - pixf.x, dy = q0.y - pixf.y;
+      const float power = splat_power(dx, dy, q0.z, q0.w, q1.x);
+      float g[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) g[i] = 0.f;
+      bool hit = false;
+      if (!(power > 0.0f) && spos <= nc) {
+        const float G = expf(power);
+        const float alpha = fminf(0.99f, __fmul_rn(q1.y, G));
+        if (!(alpha < 1.0f / 255.0f)) {
+          hit = true;
+          const float4 q2 = s_q2[j];
+          hit_update(p, g, dx, dy, G, alpha, q0.z, q0.w, q1.x, q1.y, q2.x, q2.y, q2.z, ddelx_dx, ddely_dy);
+        }
+      }
+      if (__any_sync(0xffffffffu, hit)) {
+        float g8;
+        const float tot = warp_sum9(g, lane, g8);
+        float* dst = a.acc + (size_t)s_ids[j] * ACC_STRIDE;
+        if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), tot);
+        if (lane == 1) atomicAdd(dst + 8, g8);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
+                      const float* dL_dpix, float* acc, cudaStream_t st) {
+  BwdArgs a;
+  a.ranges = im.ranges; a.point_list = b.point_list; a.records = g.records; a.tile_last = im.tile_last;
+  a.W = s.image_width; a.H = s.image_height;
+  a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
+  a.bg = s.bg; a.final_T = im.final_T; a.n_contrib = im.n_contrib; a.dL_dpix = dL_dpix; a.acc = acc;
+  const int ntiles = a.gx * a.gy;
+  if (ntiles == 0) return GSR_OK;
+  const int v = g_opt.render_bwd_variant;
+  if (v == 0) {
+    render_bwd_cta_kernel<<<dim3(a.gx, a.gy), dim3(TILE, TILE), 0, st>>>(a);
+  } else if (v == 2) {
+    const int warps = ntiles * 2;
+    render_bwd_warp_kernel<4><<<(warps + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else {
+    render_bwd_warp_kernel<8><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  }
+  g_launches++;
+  return check_launch("render_bwd", s.debug != 0, st);
+}
+
+}  // namespace gsr

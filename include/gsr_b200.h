@@ -1,0 +1,193 @@
+/* gsr_b200.h -- C ABI of the B200-native (sm_100a) differentiable 3D-Gaussian-splatting rasterizer.
+ *
+ * This is the drop-in boundary for the ONE hot path of buaacyw/GaussianEditor this repo rebuilds:
+ * the `diff_gaussian_rasterization._C` extension behind gaussiansplatting/gaussian_renderer.render().
+ * Every entry point replaces one binding of the reference's private pybind module
+ * (all paths relative to /root/reference/gaussiansplatting/submodules/diff-gaussian-rasterization/):
+ *
+ *   gsr_forward_preprocess + gsr_forward_render   <- _C.rasterize_gaussians          ext.cpp:16, rasterize_points.cu:35-95,
+ *                                                                                     cuda_rasterizer/rasterizer_impl.cu:179-285
+ *   gsr_backward                                  <- _C.rasterize_gaussians_backward ext.cpp:17, rasterize_points.cu:97-157,
+ *                                                                                     cuda_rasterizer/rasterizer_impl.cu:289-341
+ *   gsr_mark_visible                              <- _C.mark_visible                 ext.cpp:18, rasterize_points.cu:159-175
+ *   gsr_apply_weights                             <- _C.apply_weights                ext.cpp:19, rasterize_points.cu:177-234
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  Unless a parameter says "host", every pointer is a
+ *     DEVICE pointer on the current CUDA device; the caller (PyTorch's caching allocator in the Python
+ *     binding, cudaMalloc in a C host) owns all memory.  "Optional" pointers may be NULL; the reference
+ *     encodes the same thing as empty tensors (rasterizer_impl.cu:205,241,275).
+ *   - every call takes the cudaStream_t to run on (as void*); the reference always ran on the legacy
+ *     default stream and blocked on a cudaMemcpy (rasterizer_impl.cu:237) -- here the only host
+ *     synchronisation is the caller waiting for `num_rendered` between the two forward halves.
+ *   - return value: 0 = ok, <0 = error (see gsr_last_error()).  There is NO CPU fallback: without a usable
+ *     sm_100 device every compute entry point fails with GSR_ERR_CUDA.
+ *   - all floating-point data is IEEE binary32, exactly as in the reference.
+ */
+#ifndef GSR_B200_H_
+#define GSR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSR_OK 0
+#define GSR_ERR_INVALID (-1) /* bad argument combination (mirrors the reference's Python/C++ argument checks) */
+#define GSR_ERR_CUDA (-2)    /* CUDA runtime error; message in gsr_last_error() */
+#define GSR_ERR_WORKSPACE (-3) /* a workspace is smaller than the matching gsr_*_bytes() query */
+
+#define GSR_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define GSR_API __attribute__((visibility("default")))
+#else
+#define GSR_API
+#endif
+
+/* Per-call camera / configuration bundle: the fields of GaussianRasterizationSettings
+ * (diff_gaussian_rasterization/__init__.py:228-240) plus the two SH sizes the glue derives
+ * (rasterize_points.cu:73-76). */
+typedef struct gsr_settings {
+  int32_t image_height;
+  int32_t image_width;
+  float tanfovx;
+  float tanfovy;
+  float scale_modifier;
+  int32_t sh_degree;   /* D: active degree, 0..3 */
+  int32_t sh_coeffs;   /* M: coefficients ALLOCATED per Gaussian in `shs` (0 when colors_precomp is used) */
+  int32_t prefiltered; /* kept for API parity; a culled point with prefiltered!=0 is simply skipped */
+  int32_t debug;       /* !=0: synchronise and check for CUDA errors after every launch (auxiliary.h:166-173) */
+  const float* bg;         /* [3]  */
+  const float* viewmatrix; /* [16] transposed world->camera (scene/cameras.py:92)  */
+  const float* projmatrix; /* [16] transposed full projection (scene/cameras.py:93-94) */
+  const float* campos;     /* [3]  */
+} gsr_settings;
+
+/* The Gaussian cloud as the reference's forward takes it (diff_gaussian_rasterization/__init__.py:258-268).
+ * Exactly one of {shs, colors_precomp} and exactly one of {(scales, rotations), cov3D_precomp} is non-NULL. */
+typedef struct gsr_cloud {
+  int32_t P;                   /* number of Gaussians */
+  const float* means3D;        /* [P,3] */
+  const float* opacities;      /* [P,1] already sigmoid-ed */
+  const float* shs;            /* [P,M,3] optional */
+  const float* colors_precomp; /* [P,3]   optional */
+  const float* scales;         /* [P,3]   optional, already exp-ed */
+  const float* rotations;      /* [P,4]   optional, (r,x,y,z), normalised by the caller */
+  const float* cov3D_precomp;  /* [P,6]   optional */
+} gsr_cloud;
+
+/* Gradient outputs of the backward pass, shapes as rasterize_points.cu:120-128. The kernels write EVERY
+ * element (zeros for invisible Gaussians and for SH coefficients above the active degree), so the
+ * buffers may be uninitialised on entry. */
+typedef struct gsr_grads {
+  float* dL_dmeans3D;   /* [P,3] */
+  float* dL_dmeans2D;   /* [P,3] (z is always 0; x,y carry the 0.5*W / 0.5*H NDC scaling, backward.cu:460-461) */
+  float* dL_dcolors;    /* [P,3] */
+  float* dL_dopacity;   /* [P,1] */
+  float* dL_dcov3D;     /* [P,6] */
+  float* dL_dsh;        /* [P,M,3] (NULL when M == 0) */
+  float* dL_dscales;    /* [P,3] */
+  float* dL_drotations; /* [P,4] */
+} gsr_grads;
+
+GSR_API int gsr_abi_version(void);
+GSR_API const char* gsr_last_error(void); /* thread-local, valid until the next failing call on this thread */
+
+/* ---- workspace sizing (the three opaque buffers of rasterize_points.cu:62-69) ------------------------ */
+GSR_API size_t gsr_geometry_bytes(int32_t P);
+GSR_API size_t gsr_image_bytes(int32_t image_width, int32_t image_height);
+GSR_API size_t gsr_binning_bytes(int32_t P, int64_t num_rendered, int32_t image_width, int32_t image_height);
+/* scratch for the backward pass (2-D gradient accumulators) */
+GSR_API size_t gsr_backward_scratch_bytes(int32_t P);
+
+/* ---- forward, first half: per-Gaussian preprocess + depth order + tile-count scan --------------------
+ * Writes `radii` [P] int32 (0 = culled) and fills `geometry`. The total number of (Gaussian, tile)
+ * instances is copied asynchronously into *num_rendered_host (PINNED host memory, int32); the caller must
+ * synchronise `stream` (or an event recorded after this call) before reading it. */
+GSR_API int gsr_forward_preprocess(const gsr_settings* s, const gsr_cloud* c, void* geometry, size_t geometry_bytes,
+                           int32_t* radii, int32_t* num_rendered_host, void* stream);
+
+/* ---- forward, second half: instance emission, per-tile ordering, tile ranges, alpha blending ----------
+ * out_color [3,H,W], out_depth [1,H,W] (depth = sum view_z*alpha*T, no background, forward.cu:359,377). */
+GSR_API int gsr_forward_render(const gsr_settings* s, const gsr_cloud* c, int32_t num_rendered, void* geometry,
+                       size_t geometry_bytes, void* binning, size_t binning_bytes, void* image, size_t image_bytes,
+                       const int32_t* radii, float* out_color, float* out_depth, void* stream);
+
+/* ---- backward ------------------------------------------------------------------------------------------
+ * dL_dout_color [3,H,W]; the three workspaces and `radii` are the ones the forward produced. */
+GSR_API int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t num_rendered, const void* geometry,
+                 size_t geometry_bytes, const void* binning, size_t binning_bytes, const void* image,
+                 size_t image_bytes, const int32_t* radii, const float* dL_dout_color, void* scratch,
+                 size_t scratch_bytes, const gsr_grads* grads, void* stream);
+
+/* ---- markVisible: present[i] = view-space z > 0.2 (auxiliary.h:139-164) ------------------------------- */
+GSR_API int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* ---- apply_weights (semantic tracing, cuda_rasterizer/apply_weights.cu:240-356) ------------------------
+ * Second half of a forward whose colours are ignored: for every (pixel, splat) pair the forward would blend,
+ * weights[id*CH+ch] += image_weights[ch,pixel] and cnt[id] += 1 once per channel. Call
+ * gsr_forward_preprocess first (with colors_precomp = weights, as the reference does,
+ * rasterize_points.cu:223). CH = 1..3. */
+GSR_API int gsr_apply_weights(const gsr_settings* s, const gsr_cloud* c, int32_t num_rendered, void* geometry,
+                      size_t geometry_bytes, void* binning, size_t binning_bytes, void* image, size_t image_bytes,
+                      const int32_t* radii, const float* image_weights, int32_t num_channels, float* weights,
+                      int32_t* cnt, void* stream);
+
+/* ---- introspection for parity tests: device pointers into the opaque workspaces ----------------------- */
+typedef struct gsr_geometry_view {
+  const float* records;          /* [P,12]: x,y,conicA,conicB | conicC,opacity,depth,_ | r,g,b,_  (visible only) */
+  const uint32_t* tiles_touched; /* [P] */
+  const uint8_t* clamped;        /* [P] bit ch set = SH colour channel ch was clamped at 0 */
+  const uint32_t* depth_order;   /* [P] Gaussian indices ascending in (depth bits, index); culled ones last */
+} gsr_geometry_view;
+typedef struct gsr_binning_view {
+  const uint32_t* point_list; /* [R] == the reference's sorted point_list (rasterizer_impl.cu:256-261) */
+  const uint32_t* tile_keys;  /* [R] sorted tile id of each instance */
+} gsr_binning_view;
+typedef struct gsr_image_view {
+  const float* final_T;       /* [H*W] */
+  const uint32_t* n_contrib;  /* [H*W] */
+  const uint32_t* ranges;     /* [Ntile,2] */
+} gsr_image_view;
+GSR_API int gsr_view_geometry(const void* geometry, int32_t P, gsr_geometry_view* out);
+GSR_API int gsr_view_binning(const void* binning, int32_t P, int64_t num_rendered, int32_t image_width,
+                     int32_t image_height, gsr_binning_view* out);
+GSR_API int gsr_view_image(const void* image, int32_t image_width, int32_t image_height, gsr_image_view* out);
+
+/* ---- tuning / instrumentation ---------------------------------------------------------------------------
+ * gsr_set_option("render_variant", v) etc.; unknown names return GSR_ERR_INVALID.
+ * gsr_launch_count(): number of this library's kernel launches (CUB's included) since process start. */
+GSR_API int gsr_set_option(const char* name, int64_t value);
+GSR_API int64_t gsr_get_option(const char* name);
+GSR_API int64_t gsr_launch_count(void);
+
+/* Per-stage device timing (CUDA events recorded on the launching stream around each stage while the option
+ * "profile" is 1). gsr_profile_read synchronises the device, adds up the elapsed times recorded since the last
+ * read, writes GSR_NUM_STAGES milliseconds / call counts, and clears the records. */
+#define GSR_NUM_STAGES 9
+#define GSR_STAGE_NAMES "preprocess_fwd,depth_order_scan,emit_instances,tile_sort,tile_ranges,render_fwd,render_bwd,preprocess_bwd,apply_weights"
+GSR_API int gsr_profile_read(double* ms_out, int64_t* calls_out);
+
+/* ---- host-buffer convenience entry points (what a non-PyTorch host binds; used by bench.py's e2e leg) ---
+ * One persistent device context; all pointers below are HOST pointers. The cloud is uploaded once with
+ * gsr_host_upload_cloud; each gsr_host_step copies the camera + dL/dcolor image in (H2D) and the rendered
+ * image + a few gradient checksums out (D2H) inside the call. */
+typedef struct gsr_host_ctx gsr_host_ctx;
+GSR_API gsr_host_ctx* gsr_host_create(void);
+GSR_API void gsr_host_destroy(gsr_host_ctx* ctx);
+GSR_API int gsr_host_upload_cloud(gsr_host_ctx* ctx, int32_t P, int32_t M, const float* means3D, const float* opacities,
+                          const float* shs, const float* scales, const float* rotations);
+/* settings pointers (bg, viewmatrix, projmatrix, campos) are HOST here. dL_dcolor_host may be NULL (forward only).
+ * out_color_host [3,H,W] optional, out_radii_host [P] optional, grad_checksum_host[8] optional (sum of each
+ * gradient tensor, computed on the device). Returns num_rendered (>=0) or an error (<0). */
+GSR_API int64_t gsr_host_step(gsr_host_ctx* ctx, const gsr_settings* s_host, const float* dL_dcolor_host,
+                      float* out_color_host, int32_t* out_radii_host, double* grad_checksum_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSR_B200_H_ */
