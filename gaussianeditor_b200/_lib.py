@@ -54,7 +54,7 @@ class GeometryView(C.Structure):
 
 
 class BinningView(C.Structure):
-    _fields_ = [("point_list", C.c_void_p), ("tile_keys", C.c_void_p)]
+    _fields_ = [("point_list", C.c_void_p), ("tile_keys", C.c_void_p), ("tile_key_bytes", C.c_int32)]
 
 
 class ImageView(C.Structure):

@@ -53,7 +53,8 @@ StageScope::~StageScope() {
 static int validate(const gsr_settings* s, const gsr_cloud* c) {
   if (!s || !c) { set_error("null settings/cloud"); return GSR_ERR_INVALID; }
   if (c->P < 0 || s->image_width < 0 || s->image_height < 0) { set_error("negative size"); return GSR_ERR_INVALID; }
-  if (c->P > 0 && (!c->means3D || !c->opacities)) { set_error("means3D / opacities must not be null"); return GSR_ERR_INVALID; }
+  if (c->P == 0) return GSR_OK;  // nothing to read; rasterize_points.cu:72,130 short-circuit the same way
+  if (!c->means3D || !c->opacities) { set_error("means3D / opacities must not be null"); return GSR_ERR_INVALID; }
   // diff_gaussian_rasterization/__init__.py:271-283
   if ((c->shs == nullptr) == (c->colors_precomp == nullptr)) {
     set_error("Please provide excatly one of either SHs or precomputed colors!");
@@ -225,6 +226,7 @@ int gsr_view_binning(const void* binning, int32_t P, int64_t R, int32_t W, int32
   BinningWS b;
   if (!out || !carve_binning(const_cast<void*>(binning), P, R, W, H, b)) return GSR_ERR_INVALID;
   out->point_list = b.point_list; out->tile_keys = b.keys_sorted;
+  out->tile_key_bytes = ((int64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) <= 65536 && g_opt.tile_key_bits == 16) ? 2 : 4;
   return GSR_OK;
 }
 int gsr_view_image(const void* image, int32_t W, int32_t H, gsr_image_view* out) {
@@ -241,6 +243,7 @@ int gsr_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "render_bwd_variant")) g_opt.render_bwd_variant = (int)value;
   else if (!strcmp(name, "preprocess_variant")) g_opt.preprocess_variant = (int)value;
   else if (!strcmp(name, "profile")) g_opt.profile = (int)value;
+  else if (!strcmp(name, "tile_key_bits")) g_opt.tile_key_bits = (int)value;
   else { set_error("unknown option %s", name); return GSR_ERR_INVALID; }
   return GSR_OK;
 }
@@ -250,6 +253,7 @@ int64_t gsr_get_option(const char* name) {
   if (!strcmp(name, "render_bwd_variant")) return g_opt.render_bwd_variant;
   if (!strcmp(name, "preprocess_variant")) return g_opt.preprocess_variant;
   if (!strcmp(name, "profile")) return g_opt.profile;
+  if (!strcmp(name, "tile_key_bits")) return g_opt.tile_key_bits;
   return -1;
 }
 int64_t gsr_launch_count(void) { return g_launches; }

@@ -8,7 +8,7 @@
 // Here the same permutation is produced with a quarter of the traffic by splitting the key:
 //   1. stable radix sort of the P Gaussians by depth bits (32-bit keys, P items, culled ones keyed 0xFFFFFFFF),
 //   2. inclusive scan of the tile counts IN THAT ORDER -> instance offsets, R,
-//   3. emission of (tile id, Gaussian index) in depth order (warp-cooperative for large rectangles),
+//   3. emission of (tile id, Gaussian index) in depth order, one thread per instance (load-balanced search),
 //   4. stable radix sort of the R instances by tile id only (`bit` = getHigherMsb(Ntile) bits -> 2 passes over
 //      8 B/instance) -- ties keep emission order = (depth bits, index),
 //   5. tile ranges from the sorted tile ids.
@@ -51,58 +51,41 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
   rmax.y = (unsigned)min(gy, max((int)0, (int)((py + radius + TILE - 1) / TILE)));
 }
 
-// One warp per 32 consecutive depth ranks. Small rectangles are written by their own lane; rectangles with
-// more than SMALL tiles are written by the whole warp with coalesced stores (a single huge foreground splat
-// can cover thousands of tiles and would otherwise serialise one thread).
+// One thread per OUTPUT slot (instance): perfectly balanced no matter how the tile counts are distributed --
+// in depth order the few huge near-camera splats (thousands of tiles each) are adjacent ranks, so any
+// rank-to-thread or rank-to-warp assignment serialises them. Each thread finds its rank with a binary search over
+// the inclusive offsets (neighbouring threads follow the same path, so the loads are broadcasts that hit L1/L2),
+// recomputes the owner's tile rectangle and writes tile id + Gaussian index with fully coalesced stores.
 constexpr int EMIT_THREADS = 256;
-constexpr int SMALL = 8;
+template <typename KeyT>
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
+emit_instances_kernel(int P, uint32_t R, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                       const uint32_t* __restrict__ tiles_touched, const SplatRecord* __restrict__ records,
-                      const int32_t* __restrict__ radii, int gx, int gy, uint32_t* __restrict__ keys,
+                      const int32_t* __restrict__ radii, int gx, int gy, KeyT* __restrict__ keys,
                       uint32_t* __restrict__ vals) {
-  const int rank = blockIdx.x * EMIT_THREADS + threadIdx.x;
-  const int lane = threadIdx.x & 31;
-  uint32_t idx = 0, n = 0, end = 0;
-  uint2 rmin = make_uint2(0, 0), rmax = make_uint2(0, 0);
-  if (rank < P) {
-    idx = order[rank];
-    n = tiles_touched[idx];
-    if (n > 0) {
-      end = offsets[rank];
-      const float4 q0 = __ldg(reinterpret_cast<const float4*>(records + idx));
-      tile_rect(q0.x, q0.y, radii[idx], gx, gy, rmin, rmax);
-    }
+  const uint32_t s = blockIdx.x * EMIT_THREADS + threadIdx.x;
+  if (s >= R) return;
+  // smallest rank r with offsets[r] > s (offsets is the non-decreasing inclusive scan, offsets[P-1] = R > s)
+  int lo = 0, hi = P - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(offsets + mid) > s) hi = mid; else lo = mid + 1;
   }
-  uint32_t off = end - n;
-  if (n > 0 && n <= SMALL) {
-    for (uint32_t y = rmin.y; y < rmax.y; y++)
-      for (uint32_t x = rmin.x; x < rmax.x; x++) {
-        keys[off] = y * gx + x;
-        vals[off] = idx;
-        off++;
-      }
-  }
-  unsigned big = __ballot_sync(0xffffffffu, n > SMALL);
-  while (big) {
-    const int src = __ffs(big) - 1;
-    big &= big - 1;
-    const uint32_t b_idx = __shfl_sync(0xffffffffu, idx, src);
-    const uint32_t b_n = __shfl_sync(0xffffffffu, n, src);
-    const uint32_t b_off = __shfl_sync(0xffffffffu, off, src);
-    const uint32_t b_x0 = __shfl_sync(0xffffffffu, rmin.x, src);
-    const uint32_t b_y0 = __shfl_sync(0xffffffffu, rmin.y, src);
-    const uint32_t b_w = __shfl_sync(0xffffffffu, rmax.x - rmin.x, src);
-    for (uint32_t k = lane; k < b_n; k += 32) {
-      const uint32_t ry = k / b_w, rx = k - ry * b_w;
-      keys[b_off + k] = (b_y0 + ry) * gx + (b_x0 + rx);
-      vals[b_off + k] = b_idx;
-    }
-  }
+  const uint32_t idx = order[lo];
+  const uint32_t start = __ldg(offsets + lo) - tiles_touched[idx];
+  const float4 q0 = __ldg(reinterpret_cast<const float4*>(records + idx));
+  uint2 rmin, rmax;
+  tile_rect(q0.x, q0.y, radii[idx], gx, gy, rmin, rmax);
+  const uint32_t w = rmax.x - rmin.x;
+  const uint32_t k = s - start;
+  const uint32_t ry = k / w, rx = k - ry * w;
+  keys[s] = (KeyT)((rmin.y + ry) * gx + (rmin.x + rx));
+  vals[s] = idx;
 }
 
 // rasterizer_impl.cu:105-125 on 32-bit tile keys; ranges must be zeroed beforehand (:263-265)
-__global__ void tile_ranges_kernel(int L, const uint32_t* __restrict__ keys, uint2* __restrict__ ranges) {
+template <typename KeyT>
+__global__ void tile_ranges_kernel(int L, const KeyT* __restrict__ keys, uint2* __restrict__ ranges) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= L) return;
   const uint32_t cur = keys[idx];
@@ -132,10 +115,41 @@ size_t scan_temp_bytes(int P) {
   return n;
 }
 size_t tile_sort_temp_bytes(int64_t R) {
-  size_t n = 0;
+  size_t n = 0, m = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
                                   (uint32_t*)nullptr, (int)R, 0, 32);
-  return n;
+  cub::DeviceRadixSort::SortPairs(nullptr, m, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)R, 0, 16);
+  return n > m ? n : m;
+}
+
+template <typename KeyT>
+int bin_typed(const gsr_cloud& c, int R, int gx, int gy, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
+              const int32_t* radii, cudaStream_t st, bool debug) {
+  KeyT* ku = reinterpret_cast<KeyT*>(b.keys_unsorted);
+  KeyT* ks = reinterpret_cast<KeyT*>(b.keys_sorted);
+  int rc;
+  {
+    StageScope t(ST_EMIT, st);
+    emit_instances_kernel<KeyT><<<(R + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(
+        c.P, (uint32_t)R, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, ku, b.vals_unsorted);
+    g_launches++;
+    rc = check_launch("emit_instances", debug, st);
+    if (rc) return rc;
+  }
+  {
+    StageScope t(ST_TILE_SORT, st);
+    const int bit = (int)higher_msb((uint32_t)(gx * gy));
+    size_t tb = b.cub_temp_bytes;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, (const KeyT*)ku, ks, (const uint32_t*)b.vals_unsorted,
+                                                    b.point_list, R, 0, bit, st);
+    g_launches += 4;
+    if (e != cudaSuccess) return check_cuda(e, "tile sort");
+  }
+  StageScope t(ST_RANGES, st);
+  tile_ranges_kernel<KeyT><<<(R + 255) / 256, 256, 0, st>>>(R, ks, im.ranges);
+  g_launches++;
+  return check_launch("tile_ranges", debug, st);
 }
 
 }  // namespace
@@ -236,28 +250,10 @@ int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, const Geometry
   cudaError_t e = cudaMemsetAsync(im.ranges, 0, (size_t)gx * gy * sizeof(uint2), st);
   if (e != cudaSuccess) return check_cuda(e, "ranges memset");
   if (R <= 0) return GSR_OK;
-  int rc;
-  {
-    StageScope t(ST_EMIT, st);
-    emit_instances_kernel<<<(c.P + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(
-        c.P, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, b.keys_unsorted, b.vals_unsorted);
-    g_launches++;
-    rc = check_launch("emit_instances", debug, st);
-    if (rc) return rc;
-  }
-  {
-    StageScope t(ST_TILE_SORT, st);
-    const int bit = (int)higher_msb((uint32_t)(gx * gy));
-    size_t tb = b.cub_temp_bytes;
-    e = cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, (const uint32_t*)b.keys_unsorted, b.keys_sorted,
-                                        (const uint32_t*)b.vals_unsorted, b.point_list, R, 0, bit, st);
-    g_launches += 4;
-    if (e != cudaSuccess) return check_cuda(e, "tile sort");
-  }
-  StageScope t(ST_RANGES, st);
-  tile_ranges_kernel<<<(R + 255) / 256, 256, 0, st>>>(R, b.keys_sorted, im.ranges);
-  g_launches++;
-  return check_launch("tile_ranges", debug, st);
+  // tile ids fit 16 bits for every image up to 4096x4096 (65536 tiles): half the key traffic of the sort
+  if ((int64_t)gx * gy <= 65536 && g_opt.tile_key_bits == 16)
+    return bin_typed<uint16_t>(c, R, gx, gy, g, b, im, radii, st, debug);
+  return bin_typed<uint32_t>(c, R, gx, gy, g, b, im, radii, st, debug);
 }
 
 }  // namespace gsr

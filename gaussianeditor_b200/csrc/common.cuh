@@ -66,10 +66,11 @@ constexpr int ACC_STRIDE = 12;
 
 // ---- options -----------------------------------------------------------------------------------------
 struct Options {
-  int render_fwd_variant = 1;
-  int render_bwd_variant = 1;
+  int render_fwd_variant = 2;
+  int render_bwd_variant = 2;
   int preprocess_variant = 1;
   int profile = 0;
+  int tile_key_bits = 16;
 };
 enum Stage { ST_PRE_FWD = 0, ST_DEPTH_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_RENDER_FWD, ST_RENDER_BWD, ST_PRE_BWD, ST_APPLY_W };
 // RAII stage timer: records two events on `st` when profiling is on, otherwise free.

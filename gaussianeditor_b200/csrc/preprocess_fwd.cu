@@ -3,10 +3,12 @@
 //
 // Semantics follow the reference kernel preprocessCUDA (cuda_rasterizer/forward.cu:155-256 with its helpers
 // computeCov3D :118-152, computeCov2D :74-113, computeColorFromSH :20-71, and auxiliary.h:41-56,139-164).
-// The integer outputs (radii, tile counts) are discontinuous functions of the float chain, so the chain is
-// written with the SAME expression trees (GLM's column-major mat3 product order, type_mat3x3.inl:486-518;
-// ndc2Pix in fp64) and the default -fmad contraction, and is checked bit-for-bit against the reference's own
-// CUDA build on the B200 (tests/test_vs_reference_cuda.py).
+// The integer outputs (radii, tile counts) are discontinuous functions of the float chain and the conic is
+// ill-conditioned for elongated splats, so the projection / covariance chain is pinned with _rn intrinsics to
+// the exact FMA contraction nvcc produces for the reference's expression trees (GLM's column-major mat3 product
+// order, type_mat3x3.inl:486-518; ndc2Pix in fp64), decoded from the SASS of the unmodified reference build.
+// radii, tile counts, means2D, depth, conic and rgb are bit-identical to the reference's CUDA build on the B200
+// (tests/test_parity_gpu.py).
 //
 // B200-specific structure:
 //   * the 192-byte SH row of each Gaussian that survives the near-plane test is fetched by the TMA unit
@@ -26,24 +28,6 @@ constexpr int SH_ROW_WORDS = 52;  // 48 payload + 4 pad words: 208-byte rows
 struct M3 {
   float m[3][3];  // m[column][row], GLM convention
 };
-
-// GLM's mat3 * mat3 (type_mat3x3.inl:486-518): Result[c][r] = A[0][r]*B[c][0] + A[1][r]*B[c][1] + A[2][r]*B[c][2]
-__device__ __forceinline__ M3 mat_mul(const M3& A, const M3& B) {
-  M3 R;
-#pragma unroll
-  for (int c = 0; c < 3; c++)
-#pragma unroll
-    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[0][r] * B.m[c][0] + A.m[1][r] * B.m[c][1] + A.m[2][r] * B.m[c][2];
-  return R;
-}
-__device__ __forceinline__ M3 mat_t(const M3& A) {
-  M3 R;
-#pragma unroll
-  for (int c = 0; c < 3; c++)
-#pragma unroll
-    for (int r = 0; r < 3; r++) R.m[c][r] = A.m[r][c];
-  return R;
-}
 
 __device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
 
@@ -119,10 +103,10 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
   bool vis = false;
   if (live) {
     p_orig = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
-    const float* m = a.view;
-    p_view.x = m[0] * p_orig.x + m[4] * p_orig.y + m[8] * p_orig.z + m[12];
-    p_view.y = m[1] * p_orig.x + m[5] * p_orig.y + m[9] * p_orig.z + m[13];
-    p_view.z = m[2] * p_orig.x + m[6] * p_orig.y + m[10] * p_orig.z + m[14];
+    const float* m = a.view;  // transformPoint4x3 (auxiliary.h:58-66), contraction pinned like the rest
+    p_view.x = __fadd_rn(__fmaf_rn(m[8], p_orig.z, __fmaf_rn(m[0], p_orig.x, __fmul_rn(m[4], p_orig.y))), m[12]);
+    p_view.y = __fadd_rn(__fmaf_rn(m[9], p_orig.z, __fmaf_rn(m[1], p_orig.x, __fmul_rn(m[5], p_orig.y))), m[13]);
+    p_view.z = __fadd_rn(__fmaf_rn(m[10], p_orig.z, __fmaf_rn(m[2], p_orig.x, __fmul_rn(m[6], p_orig.y))), m[14]);
     vis = !(p_view.z <= 0.2f);
   }
   const bool want_sh = a.colors_precomp == nullptr;
@@ -147,14 +131,18 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     // ---- projection (forward.cu:196-200) ----
     const float* pm = a.proj;
     float4 p_hom;
-    p_hom.x = pm[0] * p_orig.x + pm[4] * p_orig.y + pm[8] * p_orig.z + pm[12];
-    p_hom.y = pm[1] * p_orig.x + pm[5] * p_orig.y + pm[9] * p_orig.z + pm[13];
-    p_hom.z = pm[2] * p_orig.x + pm[6] * p_orig.y + pm[10] * p_orig.z + pm[14];
-    p_hom.w = pm[3] * p_orig.x + pm[7] * p_orig.y + pm[11] * p_orig.z + pm[15];
-    float p_w = 1.0f / (p_hom.w + 0.0000001f);
-    float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+    p_hom.x = __fadd_rn(__fmaf_rn(pm[8], p_orig.z, __fmaf_rn(pm[0], p_orig.x, __fmul_rn(pm[4], p_orig.y))), pm[12]);
+    p_hom.y = __fadd_rn(__fmaf_rn(pm[9], p_orig.z, __fmaf_rn(pm[1], p_orig.x, __fmul_rn(pm[5], p_orig.y))), pm[13]);
+    p_hom.w = __fadd_rn(__fmaf_rn(pm[11], p_orig.z, __fmaf_rn(pm[3], p_orig.x, __fmul_rn(pm[7], p_orig.y))), pm[15]);
+    float p_w = __frcp_rn(__fadd_rn(p_hom.w, 0.0000001f));
+    float2 p_proj = make_float2(__fmul_rn(p_hom.x, p_w), __fmul_rn(p_hom.y, p_w));
 
     // ---- 3-D covariance (forward.cu:118-152); the quaternion is used as given ----
+    // From here to the conic every operation is pinned with _rn intrinsics to the exact sequence nvcc emits for
+    // the reference at sm_100a (decoded from the SASS of the unmodified build, DESIGN.md "Numerics"): every
+    // three-term product sum a0*b0 + a1*b1 + a2*b2 is fma(a2,b2, fma(a0,b0, a1*b1)), and the quaternion terms
+    // fuse exactly the products noted below. The chain feeds det = a*c - b*b, which cancels catastrophically for
+    // elongated splats, so a different (equally valid) contraction changes conics in the 4th digit.
     float cov3D[6];
     if (a.cov3D_precomp != nullptr) {
 #pragma unroll
@@ -162,61 +150,85 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     } else {
       const float3 scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
       const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
-      M3 S;
+      const float sx = __fmul_rn(scale.x, a.scale_modifier), sy = __fmul_rn(scale.y, a.scale_modifier),
+                  sz = __fmul_rn(scale.z, a.scale_modifier);
+      const float r = q.x, x = q.y, y = q.z, z = q.w;
+      const float xz = __fmul_rn(x, z), rx = __fmul_rn(r, x), rz = __fmul_rn(r, z);
+      const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+      const float e02 = __fmaf_rn(r, y, xz);    // x*z + r*y
+      const float e20 = __fmaf_rn(-r, y, xz);   // x*z - r*y
+      const float e12 = __fmaf_rn(y, z, -rx);   // y*z - r*x
+      const float e21 = __fmaf_rn(y, z, rx);    // y*z + r*x
+      const float e01 = __fmaf_rn(x, y, -rz);   // x*y - r*z
+      const float e10 = __fmaf_rn(x, y, rz);    // x*y + r*z
+      const float q00 = __fadd_rn(yy, zz);      // y*y + z*z   (plain add: both squares are shared)
+      const float q11 = __fmaf_rn(x, x, zz);    // x*x + z*z
+      const float q22 = __fmaf_rn(x, x, yy);    // x*x + y*y
+      M3 R;  // glm::mat3(...) lists columns
+      R.m[0][0] = __fadd_rn(1.f, -__fadd_rn(q00, q00)); R.m[0][1] = __fadd_rn(e01, e01); R.m[0][2] = __fadd_rn(e02, e02);
+      R.m[1][0] = __fadd_rn(e10, e10); R.m[1][1] = __fadd_rn(1.f, -__fadd_rn(q11, q11)); R.m[1][2] = __fadd_rn(e12, e12);
+      R.m[2][0] = __fadd_rn(e20, e20); R.m[2][1] = __fadd_rn(e21, e21); R.m[2][2] = __fadd_rn(1.f, -__fadd_rn(q22, q22));
+      M3 Mm;  // M = S * R: M[c][r] = s_r * R[c][r] (the zero terms of the GLM product add exact zeros)
 #pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int r = 0; r < 3; r++) S.m[c][r] = (c == r) ? 1.0f : 0.0f;
-      S.m[0][0] = a.scale_modifier * scale.x;
-      S.m[1][1] = a.scale_modifier * scale.y;
-      S.m[2][2] = a.scale_modifier * scale.z;
-      float r = q.x, x = q.y, y = q.z, z = q.w;
-      M3 R;
-      R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
-      R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
-      R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-      M3 Mm = mat_mul(S, R);
-      M3 Sigma = mat_mul(mat_t(Mm), Mm);
-      cov3D[0] = Sigma.m[0][0]; cov3D[1] = Sigma.m[0][1]; cov3D[2] = Sigma.m[0][2];
-      cov3D[3] = Sigma.m[1][1]; cov3D[4] = Sigma.m[1][2]; cov3D[5] = Sigma.m[2][2];
+      for (int c = 0; c < 3; c++) {
+        Mm.m[c][0] = __fmul_rn(sx, R.m[c][0]);
+        Mm.m[c][1] = __fmul_rn(sy, R.m[c][1]);
+        Mm.m[c][2] = __fmul_rn(sz, R.m[c][2]);
+      }
+      // Sigma = transpose(M) * M: Sigma[c][r] = M[r][0]*M[c][0] + M[r][1]*M[c][1] + M[r][2]*M[c][2]
+      auto sig = [&](int c, int r) {
+        return __fmaf_rn(Mm.m[r][2], Mm.m[c][2], __fmaf_rn(Mm.m[r][0], Mm.m[c][0], __fmul_rn(Mm.m[r][1], Mm.m[c][1])));
+      };
+      cov3D[0] = sig(0, 0); cov3D[1] = sig(0, 1); cov3D[2] = sig(0, 2);
+      cov3D[3] = sig(1, 1); cov3D[4] = sig(1, 2); cov3D[5] = sig(2, 2);
     }
 
     // ---- EWA 2-D covariance (forward.cu:74-113) ----
-    float3 t = p_view;  // transformPoint4x3(mean, viewmatrix) again in the reference; same value
-    const float limx = 1.3f * a.tan_fovx;
-    const float limy = 1.3f * a.tan_fovy;
-    const float txtz = t.x / t.z;
-    const float tytz = t.y / t.z;
-    t.x = fminf(limx, fmaxf(-limx, txtz)) * t.z;
-    t.y = fminf(limy, fmaxf(-limy, tytz)) * t.z;
-    M3 J;
-    J.m[0][0] = a.focal_x / t.z; J.m[0][1] = 0.0f; J.m[0][2] = -(a.focal_x * t.x) / (t.z * t.z);
-    J.m[1][0] = 0.0f; J.m[1][1] = a.focal_y / t.z; J.m[1][2] = -(a.focal_y * t.y) / (t.z * t.z);
-    J.m[2][0] = 0.0f; J.m[2][1] = 0.0f; J.m[2][2] = 0.0f;
     const float* vm = a.view;
-    M3 Wm;
-    Wm.m[0][0] = vm[0]; Wm.m[0][1] = vm[4]; Wm.m[0][2] = vm[8];
-    Wm.m[1][0] = vm[1]; Wm.m[1][1] = vm[5]; Wm.m[1][2] = vm[9];
-    Wm.m[2][0] = vm[2]; Wm.m[2][1] = vm[6]; Wm.m[2][2] = vm[10];
-    M3 T = mat_mul(Wm, J);
-    M3 Vrk;
-    Vrk.m[0][0] = cov3D[0]; Vrk.m[0][1] = cov3D[1]; Vrk.m[0][2] = cov3D[2];
-    Vrk.m[1][0] = cov3D[1]; Vrk.m[1][1] = cov3D[3]; Vrk.m[1][2] = cov3D[4];
-    Vrk.m[2][0] = cov3D[2]; Vrk.m[2][1] = cov3D[4]; Vrk.m[2][2] = cov3D[5];
-    M3 cov = mat_mul(mat_mul(mat_t(T), mat_t(Vrk)), T);
-    cov.m[0][0] += 0.3f;
-    cov.m[1][1] += 0.3f;
-    const float3 cov2 = make_float3(cov.m[0][0], cov.m[0][1], cov.m[1][1]);
+    float3 t = p_view;  // transformPoint4x3(mean, viewmatrix) again in the reference: same value
+    const float limx = __fmul_rn(1.3f, a.tan_fovx);
+    const float limy = __fmul_rn(1.3f, a.tan_fovy);
+    const float txtz = __fdiv_rn(t.x, t.z);
+    const float tytz = __fdiv_rn(t.y, t.z);
+    t.x = __fmul_rn(fminf(limx, fmaxf(-limx, txtz)), t.z);
+    t.y = __fmul_rn(fminf(limy, fmaxf(-limy, tytz)), t.z);
+    const float tz2 = __fmul_rn(t.z, t.z);
+    const float J00 = __fdiv_rn(a.focal_x, t.z);
+    const float J02 = __fdiv_rn(__fmul_rn(-t.x, a.focal_x), tz2);   // -(focal_x * t.x) / (t.z * t.z)
+    const float J11 = __fdiv_rn(a.focal_y, t.z);
+    const float J12 = __fdiv_rn(__fmul_rn(-t.y, a.focal_y), tz2);
+    // T = W * J with J's zero entries: T[0][r] = W[0][r]*J00 + W[2][r]*J02, T[1][r] = W[1][r]*J11 + W[2][r]*J12,
+    // W[0] = (v0,v4,v8), W[1] = (v1,v5,v9), W[2] = (v2,v6,v10)
+    const float T00 = __fmaf_rn(vm[2], J02, __fmul_rn(vm[0], J00));
+    const float T01 = __fmaf_rn(vm[6], J02, __fmul_rn(vm[4], J00));
+    const float T02 = __fmaf_rn(vm[10], J02, __fmul_rn(vm[8], J00));
+    const float T10 = __fmaf_rn(vm[2], J12, __fmul_rn(vm[1], J11));
+    const float T11 = __fmaf_rn(vm[6], J12, __fmul_rn(vm[5], J11));
+    const float T12 = __fmaf_rn(vm[10], J12, __fmul_rn(vm[9], J11));
+    const float V00 = cov3D[0], V01 = cov3D[1], V02 = cov3D[2], V11 = cov3D[3], V12 = cov3D[4], V22 = cov3D[5];
+    // A = transpose(T) * transpose(Vrk): A[c][r] = T[r][0]*V[c][0] + T[r][1]*V[c][1] + T[r][2]*V[c][2]
+    const float A00 = __fmaf_rn(T02, V02, __fmaf_rn(T00, V00, __fmul_rn(T01, V01)));
+    const float A01 = __fmaf_rn(T12, V02, __fmaf_rn(T10, V00, __fmul_rn(T11, V01)));
+    const float A10 = __fmaf_rn(T02, V12, __fmaf_rn(T00, V01, __fmul_rn(T01, V11)));
+    const float A11 = __fmaf_rn(T12, V12, __fmaf_rn(T10, V01, __fmul_rn(T11, V11)));
+    const float A20 = __fmaf_rn(T02, V22, __fmaf_rn(T00, V02, __fmul_rn(T01, V12)));
+    const float A21 = __fmaf_rn(T12, V22, __fmaf_rn(T10, V02, __fmul_rn(T11, V12)));
+    // cov = A * T: cov[c][r] = A[0][r]*T[c][0] + A[1][r]*T[c][1] + A[2][r]*T[c][2]; +0.3 low-pass on the diagonal
+    const float3 cov2 = make_float3(
+        __fadd_rn(__fmaf_rn(T02, A20, __fmaf_rn(T00, A00, __fmul_rn(T01, A10))), 0.3f),
+        __fmaf_rn(T02, A21, __fmaf_rn(T00, A01, __fmul_rn(T01, A11))),
+        __fadd_rn(__fmaf_rn(T12, A21, __fmaf_rn(T10, A01, __fmul_rn(T11, A11))), 0.3f));
 
     // ---- conic, radius, tile rectangle (forward.cu:218-237, auxiliary.h:46-56) ----
-    float det = (cov2.x * cov2.z - cov2.y * cov2.y);
+    float det = __fmaf_rn(cov2.x, cov2.z, -__fmul_rn(cov2.y, cov2.y));
     if (det != 0.0f) {
-      float det_inv = 1.f / det;
-      float3 conic = make_float3(cov2.z * det_inv, -cov2.y * det_inv, cov2.x * det_inv);
-      float mid = 0.5f * (cov2.x + cov2.z);
-      float lambda1 = mid + sqrtf(fmaxf(0.1f, mid * mid - det));
-      float lambda2 = mid - sqrtf(fmaxf(0.1f, mid * mid - det));
-      float my_radius = ceilf(3.f * sqrtf(fmaxf(lambda1, lambda2)));
+      float det_inv = __frcp_rn(det);
+      float3 conic = make_float3(__fmul_rn(cov2.z, det_inv), __fmul_rn(cov2.y, -det_inv), __fmul_rn(cov2.x, det_inv));
+      float mid = __fmul_rn(__fadd_rn(cov2.x, cov2.z), 0.5f);
+      float disc = sqrtf(fmaxf(0.1f, __fmaf_rn(mid, mid, -det)));
+      float lambda1 = __fadd_rn(mid, disc);
+      float lambda2 = __fadd_rn(mid, -disc);
+      float my_radius = ceilf(__fmul_rn(3.f, sqrtf(fmaxf(lambda1, lambda2))));
       float2 point_image = make_float2(ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H));
       const int max_radius = (int)my_radius;
       uint2 rect_min, rect_max;

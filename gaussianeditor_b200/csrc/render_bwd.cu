@@ -41,16 +41,21 @@ struct BwdArgs {
 
 // One (pixel, splat) hit. `ar*` is the reference's accum_rec updated eagerly (same operands, same order as
 // backward.cu:515), `bgT` = T_final * (bg . dL_dpixel).
+//
+// The nine sums of backward.cu:523-554 are accumulated as moments of w = dL_dG * G over the pixels,
+//   g[3..8] = sum w*{1, dx, dy, dx*dx, dx*dy, dy*dy},   g[0..2] = sum alpha*T*dL_dpixel,
+// and turned into the reference's quantities once per (tile, splat) by finish_sums() -- the per-splat factors
+// (conic, opacity, 0.5*W, 0.5*H) are constant over the pixels, so this is the same sum with the common factor
+// pulled out (8 instead of 17 operations per hit).
 struct PixState {
   float T, ar0, ar1, ar2, d0, d1, d2, bgT;
 };
 
-__device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, float dy, float G, float alpha, float A,
-                                           float B, float C, float o, float c0, float c1, float c2, float ddelx_dx,
-                                           float ddely_dy) {
+__device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, float dy, float G, float alpha, float o,
+                                           float c0, float c1, float c2) {
   const float oma = 1.f - alpha;
-  const float rcp = 1.f / oma;
-  p.T = p.T * rcp;
+  const float rcp = __fdividef(1.f, oma);  // 1-alpha in [0.01, 1]: MUFU.RCP is accurate to ~1 ulp here
+  p.T = p.T * rcp;                         // T / (1 - alpha)
   const float dchannel_dcolor = alpha * p.T;
   float dL_dalpha = (c0 - p.ar0) * p.d0;
   dL_dalpha = fmaf(c1 - p.ar1, p.d1, dL_dalpha);
@@ -62,16 +67,38 @@ __device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, floa
   p.ar1 = fmaf(alpha, c1, oma * p.ar1);
   p.ar2 = fmaf(alpha, c2, oma * p.ar2);
   dL_dalpha = fmaf(dL_dalpha, p.T, -p.bgT * rcp);
-  const float dL_dG = o * dL_dalpha;
-  const float gdx = G * dx, gdy = G * dy;
-  const float dG_ddelx = -gdx * A - gdy * B;
-  const float dG_ddely = -gdy * C - gdx * B;
-  g[3] = fmaf(dL_dG * dG_ddelx, ddelx_dx, g[3]);
-  g[4] = fmaf(dL_dG * dG_ddely, ddely_dy, g[4]);
-  g[5] = fmaf(-0.5f * gdx * dx, dL_dG, g[5]);
-  g[6] = fmaf(-0.5f * gdx * dy, dL_dG, g[6]);
-  g[7] = fmaf(-0.5f * gdy * dy, dL_dG, g[7]);
-  g[8] = fmaf(G, dL_dalpha, g[8]);
+  const float w = (o * dL_dalpha) * G;  // dL_dG * G
+  const float wdx = w * dx, wdy = w * dy;
+  g[3] += w;
+  g[4] += wdx;
+  g[5] += wdy;
+  g[6] = fmaf(wdx, dx, g[6]);
+  g[7] = fmaf(wdx, dy, g[7]);
+  g[8] = fmaf(wdy, dy, g[8]);
+}
+
+// Warp totals of the moments -> the reference's nine gradient contributions, for the lane that owns output j
+// (acc layout: 0..2 dcolor, 3..4 dmean2D, 5..7 dconic a,b,c, 8 dopacity). `tot` is the total of moment (lane>>2)
+// on lanes 0,4,..,28 and m8 = sum w*dy*dy on every lane; the other moments are fetched with shuffles.
+__device__ __forceinline__ void finish_and_add(float* dst, float tot, float m8, int lane, float A, float B, float C,
+                                               float o, float ddelx_dx, float ddely_dy) {
+  const unsigned F = 0xffffffffu;
+  const float s_w = __shfl_sync(F, tot, 12);   // moment 3: sum w
+  const float s_x = __shfl_sync(F, tot, 16);   // moment 4: sum w*dx
+  const float s_y = __shfl_sync(F, tot, 20);   // moment 5: sum w*dy
+  const float s_xx = __shfl_sync(F, tot, 24);  // moment 6
+  const float s_xy = __shfl_sync(F, tot, 28);  // moment 7
+  float v;
+  switch (lane >> 2) {
+    case 0: case 1: case 2: v = tot; break;                          // dL/dcolor
+    case 3: v = -(s_x * A + s_y * B) * ddelx_dx; break;             // dL/dmean2D.x = sum dL_dG*dG_ddelx*0.5W
+    case 4: v = -(s_y * C + s_x * B) * ddely_dy; break;             // dL/dmean2D.y
+    case 5: v = -0.5f * s_xx; break;                                 // dL/dconic.a
+    case 6: v = -0.5f * s_xy; break;                                 // dL/dconic.b
+    default: v = -0.5f * m8; break;                                  // dL/dconic.c
+  }
+  if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), v);
+  if (lane == 1) atomicAdd(dst + 8, __fdividef(s_w, o));             // dL/dopacity = sum G*dL_dalpha = sum w / o
 }
 
 // Sum nine per-lane values over the warp. g[0..7] go through a transposing butterfly: after it, lane 4*j (and
@@ -254,14 +281,12 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
         const float alpha = fminf(0.99f, __fmul_rn(s1.y, G));
         if (alpha < 1.0f / 255.0f) continue;
         any = true;
-        hit_update(ps[k], g, dx, dy, G, alpha, s0.z, s0.w, s1.x, s1.y, s2.x, s2.y, s2.z, ddelx_dx, ddely_dy);
+        hit_update(ps[k], g, dx, dy, G, alpha, s1.y, s2.x, s2.y, s2.z);
       }
       if (__any_sync(0xffffffffu, any)) {
-        float g8;
-        const float tot = warp_sum9(g, lane, g8);
-        float* dst = a.acc + (size_t)sid[j] * ACC_STRIDE;
-        if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), tot);
-        if (lane == 1) atomicAdd(dst + 8, g8);
+        float m8;
+        const float tot = warp_sum9(g, lane, m8);
+        finish_and_add(a.acc + (size_t)sid[j] * ACC_STRIDE, tot, m8, lane, s0.z, s0.w, s1.x, s1.y, ddelx_dx, ddely_dy);
       }
     }
     __syncwarp();
@@ -323,15 +348,13 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs 
         if (!(alpha < 1.0f / 255.0f)) {
           hit = true;
           const float4 q2 = s_q2[j];
-          hit_update(p, g, dx, dy, G, alpha, q0.z, q0.w, q1.x, q1.y, q2.x, q2.y, q2.z, ddelx_dx, ddely_dy);
+          hit_update(p, g, dx, dy, G, alpha, q1.y, q2.x, q2.y, q2.z);
         }
       }
       if (__any_sync(0xffffffffu, hit)) {
-        float g8;
-        const float tot = warp_sum9(g, lane, g8);
-        float* dst = a.acc + (size_t)s_ids[j] * ACC_STRIDE;
-        if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), tot);
-        if (lane == 1) atomicAdd(dst + 8, g8);
+        float m8;
+        const float tot = warp_sum9(g, lane, m8);
+        finish_and_add(a.acc + (size_t)s_ids[j] * ACC_STRIDE, tot, m8, lane, q0.z, q0.w, q1.x, q1.y, ddelx_dx, ddely_dy);
       }
     }
   }
@@ -354,6 +377,9 @@ int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningW
   } else if (v == 2) {
     const int warps = ntiles * 2;
     render_bwd_warp_kernel<4><<<(warps + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 3) {
+    const int warps = ntiles * 4;
+    render_bwd_warp_kernel<2><<<(warps + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   } else {
     render_bwd_warp_kernel<8><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   }

@@ -309,7 +309,7 @@ def forward_state_views(state: _ForwardState):
         bv = _lib.BinningView()
         _lib.check(lib.gsr_view_binning(_ptr(state.binning), P, R, W, H, C.byref(bv)), "gsr_view_binning")
         out["point_list"] = view(bv.point_list, state.binning, R, torch.int32)
-        out["tile_keys"] = view(bv.tile_keys, state.binning, R, torch.int32)
+        out["tile_keys"] = view(bv.tile_keys, state.binning, R, torch.int16 if bv.tile_key_bytes == 2 else torch.int32)
     else:
         out["point_list"] = torch.empty(0, dtype=torch.int32, device=state.geom.device)
         out["tile_keys"] = torch.empty(0, dtype=torch.int32, device=state.geom.device)

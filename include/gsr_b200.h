@@ -146,7 +146,8 @@ typedef struct gsr_geometry_view {
 } gsr_geometry_view;
 typedef struct gsr_binning_view {
   const uint32_t* point_list; /* [R] == the reference's sorted point_list (rasterizer_impl.cu:256-261) */
-  const uint32_t* tile_keys;  /* [R] sorted tile id of each instance */
+  const void* tile_keys;      /* [R] sorted tile id of each instance, uint16 or uint32 (tile_key_bytes) */
+  int32_t tile_key_bytes;
 } gsr_binning_view;
 typedef struct gsr_image_view {
   const float* final_T;       /* [H*W] */

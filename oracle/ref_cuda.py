@@ -44,6 +44,8 @@ def lib():
             [C.c_void_p] * 3 + [C.c_int]
         L.dgr_state_ptrs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.dgr_last_cuda_error.restype = C.c_int
+        L.dgr_copy_d2d.restype = C.c_int
+        L.dgr_copy_d2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
 
@@ -114,9 +116,9 @@ class ReferenceRasterizer:
         def copy(ptr, numel, dtype):
             out = torch.empty(numel, dtype=dtype, device=dev)
             if numel and ptr:
-                torch.cuda.synchronize()
-                rc = torch.cuda.cudart().cudaMemcpy(out.data_ptr(), ptr, out.numel() * out.element_size(), 3)
-                assert int(rc) == 0
+                rc = self.L.dgr_copy_d2d(C.c_void_p(out.data_ptr()), C.c_void_p(ptr),
+                                         C.c_size_t(out.numel() * out.element_size()))
+                assert int(rc) == 0, rc
             return out
         ntile = ((W + 15) // 16) * ((H + 15) // 16)
         return dict(

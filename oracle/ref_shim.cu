@@ -118,3 +118,10 @@ REF_API void dgr_state_ptrs(void* c, int P, int W, int H, int R, void** out) {
 }
 
 REF_API int dgr_last_cuda_error() { return (int)cudaGetLastError(); }
+
+// device->device copy of an intermediate into a caller-owned buffer (after a full device sync)
+REF_API int dgr_copy_d2d(void* dst, const void* src, size_t bytes) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice);
+  return (int)e;
+}

@@ -60,7 +60,7 @@ def compare(name, cloud, cam, bg, fv, bv):
 
 try:
     for name, cloud, cam, bg in T._small_cases():
-        for fv, bv in [(0, 0), (1, 1), (1, 2)]:
+        for fv, bv in [(0, 0), (2, 2), (3, 3)]:
             key = f"{name}_f{fv}_b{bv}"
             try:
                 report[key] = compare(name, cloud, cam, bg, fv, bv)
@@ -90,8 +90,8 @@ try:
         return a.elapsed_time(b) / n
 
     ours = bench.OursRunner(wl)
-    for fv in [0, 1]:
-        for bv in [0, 1, 2]:
+    for fv, bv in [(1, 1), (2, 2), (3, 3)]:
+        if True:
             _lib.set_option("render_fwd_variant", fv)
             _lib.set_option("render_bwd_variant", bv)
             ms = time_runner(ours)
@@ -101,16 +101,16 @@ try:
             prof = _lib.profile_read(); _lib.set_option("profile", 0)
             timing[f"ours_f{fv}_b{bv}"] = dict(ms_per_step=ms, stages={k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1]})
             print(f"ours_f{fv}_b{bv}", json.dumps(timing[f"ours_f{fv}_b{bv}"]), flush=True)
-    _lib.set_option("render_fwd_variant", 1); _lib.set_option("render_bwd_variant", 1)
-    for pv in [0, 1]:
-        _lib.set_option("preprocess_variant", pv)
+    _lib.set_option("render_fwd_variant", 2); _lib.set_option("render_bwd_variant", 2)
+    for pv in [32, 16]:
+        _lib.set_option("tile_key_bits", pv)
         _lib.set_option("profile", 1); _lib.profile_read()
         for i in range(8):
             ours.step(i)
         prof = _lib.profile_read(); _lib.set_option("profile", 0)
         timing[f"ours_pre{pv}"] = {k: v[0] / max(v[1], 1) for k, v in prof.items() if v[1]}
         print(f"ours_pre{pv}", json.dumps(timing[f"ours_pre{pv}"]), flush=True)
-    _lib.set_option("preprocess_variant", 1)
+    _lib.set_option("tile_key_bits", 16)
     timing["workload"] = ours.describe()
     if ref_cuda.available():
         refr = bench.ReferenceCudaRunner(wl)
