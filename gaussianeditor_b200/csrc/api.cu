@@ -12,6 +12,7 @@
 namespace gsr {
 
 Options g_opt;
+unsigned long long* g_stats_dev = nullptr;
 long long g_launches = 0;
 static thread_local char g_err[512] = "";
 
@@ -244,11 +245,29 @@ int gsr_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "preprocess_variant")) g_opt.preprocess_variant = (int)value;
   else if (!strcmp(name, "profile")) g_opt.profile = (int)value;
   else if (!strcmp(name, "tile_key_bits")) g_opt.tile_key_bits = (int)value;
+  else if (!strcmp(name, "stats")) {
+    if (value && !g_stats_dev) {
+      if (cudaMalloc((void**)&g_stats_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) return check_cuda(cudaGetLastError(), "stats alloc");
+      cudaMemset(g_stats_dev, 0, 16 * sizeof(unsigned long long));
+    } else if (!value && g_stats_dev) {
+      cudaFree(g_stats_dev);
+      g_stats_dev = nullptr;
+    }
+  }
   else { set_error("unknown option %s", name); return GSR_ERR_INVALID; }
   return GSR_OK;
 }
 int64_t gsr_get_option(const char* name) {
   if (!name) return -1;
+  if (!strncmp(name, "stat", 4) && name[4] >= '0' && name[4] <= '9') {  // "stat0".."stat9": read + clear a counter
+    if (!g_stats_dev) return -1;
+    unsigned long long v = 0, z = 0;
+    const int i = name[4] - '0';
+    cudaDeviceSynchronize();
+    cudaMemcpy(&v, g_stats_dev + i, sizeof(v), cudaMemcpyDeviceToHost);
+    cudaMemcpy(g_stats_dev + i, &z, sizeof(z), cudaMemcpyHostToDevice);
+    return (int64_t)v;
+  }
   if (!strcmp(name, "render_fwd_variant")) return g_opt.render_fwd_variant;
   if (!strcmp(name, "render_bwd_variant")) return g_opt.render_bwd_variant;
   if (!strcmp(name, "preprocess_variant")) return g_opt.preprocess_variant;

@@ -53,9 +53,11 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
 
 // One thread per OUTPUT slot (instance): perfectly balanced no matter how the tile counts are distributed --
 // in depth order the few huge near-camera splats (thousands of tiles each) are adjacent ranks, so any
-// rank-to-thread or rank-to-warp assignment serialises them. Each thread finds its rank with a binary search over
-// the inclusive offsets (neighbouring threads follow the same path, so the loads are broadcasts that hit L1/L2),
-// recomputes the owner's tile rectangle and writes tile id + Gaussian index with fully coalesced stores.
+// rank-to-thread or rank-to-warp assignment serialises them. Finding the owner rank of a slot is a search over the
+// inclusive offsets; a per-thread binary search is a chain of ~20 dependent loads, so each WARP instead locates the
+// rank of its first slot with a 32-ary cooperative search (4 dependent loads for P = 1M), probes the next 32 offsets
+// once (32 consecutive slots span at most 32 visible ranks) and the lanes finish with a shuffle-only search.
+// Stores are fully coalesced.
 constexpr int EMIT_THREADS = 256;
 template <typename KeyT>
 __global__ void __launch_bounds__(EMIT_THREADS)
@@ -63,24 +65,43 @@ emit_instances_kernel(int P, uint32_t R, const uint32_t* __restrict__ order, con
                       const uint32_t* __restrict__ tiles_touched, const SplatRecord* __restrict__ records,
                       const int32_t* __restrict__ radii, int gx, int gy, KeyT* __restrict__ keys,
                       uint32_t* __restrict__ vals) {
-  const uint32_t s = blockIdx.x * EMIT_THREADS + threadIdx.x;
-  if (s >= R) return;
-  // smallest rank r with offsets[r] > s (offsets is the non-decreasing inclusive scan, offsets[P-1] = R > s)
-  int lo = 0, hi = P - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(offsets + mid) > s) hi = mid; else lo = mid + 1;
+  const unsigned F = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const uint32_t s0 = (blockIdx.x * EMIT_THREADS + threadIdx.x) - lane;  // first slot of this warp
+  if (s0 >= R) return;
+  // smallest rank r0 with offsets[r0] > s0; invariant: answer in [lo, lo+n), offsets[lo+n-1] > s0
+  int lo = 0, n = P;
+  while (n > 1) {  // warp-uniform
+    const int stride = (n + 31) >> 5;
+    const int pos = min(lo + (lane + 1) * stride - 1, lo + n - 1);
+    const unsigned gt = __ballot_sync(F, __ldg(offsets + pos) > s0);
+    const int j = __ffs(gt) - 1;
+    lo += j * stride;
+    n = min(stride, n - j * stride);
   }
-  const uint32_t idx = order[lo];
-  const uint32_t start = __ldg(offsets + lo) - tiles_touched[idx];
+  const int r0 = lo;
+  const uint32_t oj = __ldg(offsets + min(r0 + lane, P - 1));
+  const uint32_t s = min(s0 + lane, R - 1);
+  int c = 0;  // number of probed offsets <= s  (0..31)
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const uint32_t e = __shfl_sync(F, oj, c + step - 1);
+    if (e <= s) c += step;
+  }
+  const uint32_t end = __shfl_sync(F, oj, c);
+  const int rank = min(r0 + c, P - 1);
+  const uint32_t idx = order[rank];
+  const uint32_t start = end - tiles_touched[idx];
   const float4 q0 = __ldg(reinterpret_cast<const float4*>(records + idx));
   uint2 rmin, rmax;
   tile_rect(q0.x, q0.y, radii[idx], gx, gy, rmin, rmax);
-  const uint32_t w = rmax.x - rmin.x;
+  const uint32_t w = max(rmax.x - rmin.x, 1u);
   const uint32_t k = s - start;
   const uint32_t ry = k / w, rx = k - ry * w;
-  keys[s] = (KeyT)((rmin.y + ry) * gx + (rmin.x + rx));
-  vals[s] = idx;
+  if (s0 + lane < R) {
+    keys[s] = (KeyT)((rmin.y + ry) * gx + (rmin.x + rx));
+    vals[s] = idx;
+  }
 }
 
 // rasterizer_impl.cu:105-125 on 32-bit tile keys; ranges must be zeroed beforehand (:263-265)

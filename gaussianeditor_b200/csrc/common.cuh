@@ -66,8 +66,8 @@ constexpr int ACC_STRIDE = 12;
 
 // ---- options -----------------------------------------------------------------------------------------
 struct Options {
-  int render_fwd_variant = 2;
-  int render_bwd_variant = 2;
+  int render_fwd_variant = 3;  // 0 CTA/tile, 1/2/3 = 1/2/4 warps per tile
+  int render_bwd_variant = 4;  // 0 CTA/tile, 1/2/3 branchy 1/2/4 warps per tile, 4/5/6/7 branch-light variants
   int preprocess_variant = 1;
   int profile = 0;
   int tile_key_bits = 16;
@@ -80,6 +80,7 @@ struct StageScope {
   ~StageScope();
 };
 extern Options g_opt;
+extern unsigned long long* g_stats_dev;  // device counters when option "stats" is on (instrumentation only)
 extern long long g_launches;
 
 // ---- error plumbing ------------------------------------------------------------------------------------
@@ -117,6 +118,39 @@ __device__ __forceinline__ float splat_power(float dx, float dy, float A, float 
   float t2 = __fmul_rn(__fmul_rn(dx, B), dy);
   float s = __fmaf_rn(dx, t1, t0);
   return __fmaf_rn(s, -0.5f, -t2);
+}
+
+// Which 8x4 sub-blocks of tile (X0,Y0) can a splat reach with alpha >= 1/255?  alpha = o*exp(power) >= 1/255 iff
+// q(dx,dy) = A dx^2 + 2B dx dy + C dy^2 <= 2 ln(255 o), so sub-block k is reachable iff the minimum of the convex
+// quadratic q over its pixel rectangle is below that threshold. The exact box minimum of a convex quadratic whose
+// unconstrained minimiser is the origin is min(q on the line v = v_c, q on the line u = u_c) with (u_c, v_c) the box
+// point closest to the origin and the free coordinate clamped to the box (two 1-D parabola minima). The rectangle is
+// grown by 0.02 px and the threshold by 0.1 % + 2e-3, far beyond fp32 rounding of `power`, so the test only ever
+// rejects splats every pixel of the sub-block would skip at `alpha < 1/255` (results unchanged, n_contrib included).
+// Returns a mask over this warp's NSB sub-blocks (global sub-block index part*NSB + k, column k&1, row pair k>>1).
+template <int NSB>
+__device__ __forceinline__ uint32_t splat_subblock_mask(const float4 q0, const float4 q1, float X0, float Y0, int part) {
+  const float A = q0.z, B = q0.w, C = q1.x, o = q1.y;
+  if (o < 1.0f / 255.0f) return 0u;  // alpha = o*exp(power<=0) can never reach 1/255
+  const float det = A * C - B * B;
+  if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f) || !(A < 1e30f) || !(C < 1e30f)) return (1u << NSB) - 1u;
+  const float thr = 2.0f * (__logf(o * 255.0f) * 1.001f + 1e-3f);
+  const float nBA = -B / A, nBC = -B / C;
+  const float cx = q0.x - X0, cy = q0.y - Y0;  // splat centre relative to the tile origin
+  uint32_t mask = 0;
+#pragma unroll
+  for (int k = 0; k < NSB; k++) {
+    const int kg = part * NSB + k;
+    const float ua = (float)(8 * (kg & 1)) - 0.02f - cx, ub = ua + 7.04f;   // u = pixel_x - centre_x over the block
+    const float va = (float)(4 * (kg >> 1)) - 0.02f - cy, vb = va + 3.04f;
+    const float uc = fminf(fmaxf(0.f, ua), ub), vc = fminf(fmaxf(0.f, va), vb);
+    const float us = fminf(fmaxf(nBA * vc, ua), ub);                          // argmin_u q(u, vc) over [ua, ub]
+    const float vs = fminf(fmaxf(nBC * uc, va), vb);                          // argmin_v q(uc, v) over [va, vb]
+    const float q1v = A * us * us + (2.0f * B * us + C * vc) * vc;
+    const float q2v = C * vs * vs + (2.0f * B * vs + A * uc) * uc;
+    if (fminf(q1v, q2v) <= thr) mask |= 1u << k;
+  }
+  return mask;
 }
 
 // 128-bit streaming loads/stores

@@ -54,18 +54,21 @@ struct PixState {
 __device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, float dy, float G, float alpha, float o,
                                            float c0, float c1, float c2) {
   const float oma = 1.f - alpha;
-  const float rcp = __fdividef(1.f, oma);  // 1-alpha in [0.01, 1]: MUFU.RCP is accurate to ~1 ulp here
+  float rcp;  // 1-alpha is in [0.01, 1]: the bare MUFU.RCP (<= 1 ulp here) needs no range fix-up
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rcp) : "f"(oma));
+  rcp = alpha > 0.f ? rcp : 1.0f;          // (alpha, G) = (0, 0) encodes "no hit" in the branch-light variants: exact no-op
   p.T = p.T * rcp;                         // T / (1 - alpha)
   const float dchannel_dcolor = alpha * p.T;
-  float dL_dalpha = (c0 - p.ar0) * p.d0;
-  dL_dalpha = fmaf(c1 - p.ar1, p.d1, dL_dalpha);
-  dL_dalpha = fmaf(c2 - p.ar2, p.d2, dL_dalpha);
+  const float e0 = c0 - p.ar0, e1 = c1 - p.ar1, e2 = c2 - p.ar2;
+  float dL_dalpha = e0 * p.d0;
+  dL_dalpha = fmaf(e1, p.d1, dL_dalpha);
+  dL_dalpha = fmaf(e2, p.d2, dL_dalpha);
   g[0] = fmaf(dchannel_dcolor, p.d0, g[0]);
   g[1] = fmaf(dchannel_dcolor, p.d1, g[1]);
   g[2] = fmaf(dchannel_dcolor, p.d2, g[2]);
-  p.ar0 = fmaf(alpha, c0, oma * p.ar0);
-  p.ar1 = fmaf(alpha, c1, oma * p.ar1);
-  p.ar2 = fmaf(alpha, c2, oma * p.ar2);
+  p.ar0 = fmaf(alpha, e0, p.ar0);          // alpha*c + (1-alpha)*accum_rec, written as accum_rec + alpha*(c - accum_rec)
+  p.ar1 = fmaf(alpha, e1, p.ar1);
+  p.ar2 = fmaf(alpha, e2, p.ar2);
   dL_dalpha = fmaf(dL_dalpha, p.T, -p.bgT * rcp);
   const float w = (o * dL_dalpha) * G;  // dL_dG * G
   const float wdx = w * dx, wdy = w * dy;
@@ -140,29 +143,6 @@ __device__ __forceinline__ float warp_sum9(const float* g, int lane, float& g8) 
   return c;
 }
 
-// Same test as the forward's (render_fwd.cu); duplicated so each translation unit stays self-contained.
-__device__ __forceinline__ uint32_t subblock_mask_bwd(const float4 q0, const float4 q1, float X0, float Y0) {
-  const float A = q0.z, B = q0.w, C = q1.x, o = q1.y;
-  if (o < 1.0f / 255.0f) return 0u;
-  const float det = A * C - B * B;
-  if (!(det > 0.0f) || !(A > 0.0f) || !(C > 0.0f)) return 0xFFu;
-  const float tau2 = 2.0f * (__logf(o * 255.0f) * 1.001f + 1e-3f);
-  const float inv = tau2 / det;
-  const float ex = sqrtf(inv * C) * 1.001f + 0.02f;
-  const float ey = sqrtf(inv * A) * 1.001f + 0.02f;
-  if (!(ex < 1e30f) || !(ey < 1e30f)) return 0xFFu;
-  const float xlo = q0.x - ex - X0, xhi = q0.x + ex - X0;
-  const float ylo = q0.y - ey - Y0, yhi = q0.y + ey - Y0;
-  uint32_t cols = 0, rows = 0;
-  if (xhi >= 0.f && xlo <= 7.f) cols |= 0x55u;
-  if (xhi >= 8.f && xlo <= 15.f) cols |= 0xAAu;
-  if (yhi >= 0.f && ylo <= 3.f) rows |= 0x03u;
-  if (yhi >= 4.f && ylo <= 7.f) rows |= 0x0Cu;
-  if (yhi >= 8.f && ylo <= 11.f) rows |= 0x30u;
-  if (yhi >= 12.f && ylo <= 15.f) rows |= 0xC0u;
-  return cols & rows;
-}
-
 // ------------------------------------------------------------------------------------------------------
 // Variant 1: NSB sub-blocks per warp (8 = one warp per tile, 4 = two warps per tile)
 // ------------------------------------------------------------------------------------------------------
@@ -226,7 +206,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
       q0 = __ldg(r);
       q1 = __ldg(r + 1);
       q2 = __ldg(r + 2);
-      mask = (subblock_mask_bwd(q0, q1, X0, Y0) >> (part * NSB)) & ((1u << NSB) - 1u);
+      mask = splat_subblock_mask<NSB>(q0, q1, X0, Y0, part);
     }
     const uint32_t keep = __ballot_sync(0xffffffffu, mask != 0);
     const int cnt = __popc(keep);
@@ -288,6 +268,153 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
         const float tot = warp_sum9(g, lane, m8);
         finish_and_add(a.acc + (size_t)sid[j] * ACC_STRIDE, tot, m8, lane, s0.z, s0.w, s1.x, s1.y, ddelx_dx, ddely_dy);
       }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Variant 4/5: same mapping as variant 2 (NSB sub-blocks per warp) with a branch-light inner body.
+// The profile of variant 2 is latency-bound (33 % of the stall samples are fixed-latency dependency waits, 11 % branch
+// resolution, 16 warps/SM): here the NSB evaluations of a splat are issued as independent straight-line chains
+// (instruction-level parallelism NSB), hit / no-hit is folded into (alpha, G) = (0, 0) so the gradient arithmetic
+// needs no per-pixel branch, and G uses ex2.approx -- the skip decision alpha < 1/255 still equals the forward's
+// (which uses libdevice expf) because evaluations within 1e-5 of the threshold are re-done with expf.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int NSB, int MINB>
+__global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(const BwdArgs a, const int ntiles) {
+  __shared__ float4 s_stage[BW_WARPS][3][32];
+  __shared__ uint32_t s_id[BW_WARPS][32];
+  constexpr int PARTS = 8 / NSB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * BW_WARPS + warp;
+  const int tile = gw / PARTS, part = gw % PARTS;
+  if (tile >= ntiles) return;
+  float4(*stg)[32] = s_stage[warp];
+  uint32_t* sid = s_id[warp];
+
+  const int tx = tile % a.gx, ty = tile / a.gx;
+  const int lx = lane & 7, ly = lane >> 3;
+  const float X0 = (float)(tx * TILE), Y0 = (float)(ty * TILE);
+  const float fx = X0 + (float)lx, fy = Y0 + (float)ly;
+  const uint2 range = a.ranges[tile];
+  if (a.tile_last[tile] == 0) return;
+  const size_t HW = (size_t)a.H * a.W;
+  const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
+  const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+
+  PixState ps[NSB];
+  uint32_t nc[NSB], sblast[NSB];
+  uint32_t my_last = 0;
+#pragma unroll
+  for (int k = 0; k < NSB; k++) {
+    const int kg = part * NSB + k;
+    const int px = tx * TILE + 8 * (kg & 1) + lx, py = ty * TILE + 4 * (kg >> 1) + ly;
+    PixState p;
+    p.T = 0.f; p.ar0 = p.ar1 = p.ar2 = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
+    nc[k] = 0;
+    if (px < a.W && py < a.H) {
+      const size_t pix_id = (size_t)a.W * py + px;
+      const float Tf = a.final_T[pix_id];
+      p.T = Tf;
+      p.d0 = a.dL_dpix[pix_id];
+      p.d1 = a.dL_dpix[HW + pix_id];
+      p.d2 = a.dL_dpix[2 * HW + pix_id];
+      p.bgT = Tf * (bg0 * p.d0 + bg1 * p.d1 + bg2 * p.d2);
+      nc[k] = a.n_contrib[pix_id];
+    }
+    ps[k] = p;
+    sblast[k] = __reduce_max_sync(0xffffffffu, nc[k]);
+    my_last = max(my_last, sblast[k]);
+  }
+
+  for (int hi = (int)my_last; hi > 0; hi -= 32) {
+    const int pos = hi - lane;
+    uint32_t mask = 0, id = 0;
+    float4 q0, q1, q2;
+    if (pos >= 1) {
+      id = a.point_list[range.x + pos - 1];
+      const float4* r = reinterpret_cast<const float4*>(a.records + id);
+      q0 = __ldg(r);
+      q1 = __ldg(r + 1);
+      q2 = __ldg(r + 2);
+      mask = splat_subblock_mask<NSB>(q0, q1, X0, Y0, part);
+    }
+    const uint32_t keep = __ballot_sync(0xffffffffu, mask != 0);
+    const int cnt = __popc(keep);
+    if (mask != 0) {
+      const int slot = __popc(keep & ((1u << lane) - 1u));
+      q1.w = __uint_as_float(mask);
+      q2.w = __uint_as_float((uint32_t)pos);
+      stg[0][slot] = q0;
+      stg[1][slot] = q1;
+      stg[2][slot] = q2;
+      sid[slot] = id;
+    }
+    __syncwarp();
+    const uint32_t lo = (uint32_t)max(hi - 31, 1);
+    uint32_t act = 0;
+#pragma unroll
+    for (int k = 0; k < NSB; k++)
+      if (sblast[k] >= lo) act |= 1u << k;
+
+    for (int j = 0; j < cnt; j++) {
+      const float4 s1 = stg[1][j];
+      const uint32_t m = __float_as_uint(s1.w) & act;
+      if (m == 0) continue;
+      const float4 s0 = stg[0][j];
+      const float4 s2 = stg[2][j];
+      const uint32_t spos = __float_as_uint(s2.w);
+      float dxv[2], dxA[2], dxB[2], dyv[NSB / 2], t0[NSB / 2];
+#pragma unroll
+      for (int c = 0; c < 2; c++) {
+        dxv[c] = s0.x - (fx + 8.0f * c);
+        dxA[c] = __fmul_rn(dxv[c], s0.z);
+        dxB[c] = __fmul_rn(dxv[c], s0.w);
+      }
+#pragma unroll
+      for (int r = 0; r < NSB / 2; r++) {
+        dyv[r] = s0.y - (fy + 4.0f * (float)(part * (NSB / 2) + r));
+        t0[r] = __fmul_rn(__fmul_rn(dyv[r], s1.x), dyv[r]);
+      }
+      // ---- NSB independent evaluations ----
+      float G[NSB], al[NSB];
+      bool anyhit = false;
+#pragma unroll
+      for (int k = 0; k < NSB; k++) {
+        const int c = k & 1, r = k >> 1;
+        const float s = __fmaf_rn(dxv[c], dxA[c], t0[r]);
+        const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(dxB[c], dyv[r]));
+        bool ok = ((m >> k) & 1u) && !(power > 0.0f) && spos <= nc[k];
+        float Gf = ex2_approx(power * 1.4426950408889634f);
+        float af = fminf(0.99f, s1.y * Gf);
+        if (ok && fabsf(af - 1.0f / 255.0f) <= (1.0f / 255.0f) * 1e-5f) {  // too close to call: the forward's arithmetic
+          Gf = expf(power);
+          af = fminf(0.99f, __fmul_rn(s1.y, Gf));
+        }
+        ok = ok && !(af < 1.0f / 255.0f);
+        G[k] = ok ? Gf : 0.f;
+        al[k] = ok ? af : 0.f;
+        anyhit |= ok;
+      }
+      if (!__any_sync(0xffffffffu, anyhit)) continue;
+      float g[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) g[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < NSB; k++) {
+        // (alpha, G) = (0, 0) makes every update below an exact no-op: 1/(1-0) = 1, +0 contributions
+        hit_update(ps[k], g, dxv[k & 1], dyv[k >> 1], G[k], al[k], s1.y, s2.x, s2.y, s2.z);
+      }
+      float m8;
+      const float tot = warp_sum9(g, lane, m8);
+      finish_and_add(a.acc + (size_t)sid[j] * ACC_STRIDE, tot, m8, lane, s0.z, s0.w, s1.x, s1.y, ddelx_dx, ddely_dy);
     }
     __syncwarp();
   }
@@ -380,6 +507,14 @@ int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningW
   } else if (v == 3) {
     const int warps = ntiles * 4;
     render_bwd_warp_kernel<2><<<(warps + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 4) {
+    render_bwd_flat_kernel<4, 1><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 5) {
+    render_bwd_flat_kernel<4, 6><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 6) {
+    render_bwd_flat_kernel<2, 1><<<(ntiles * 4 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 7) {
+    render_bwd_flat_kernel<8, 1><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   } else {
     render_bwd_warp_kernel<8><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   }

@@ -293,6 +293,14 @@ def forward_state_views(state: _ForwardState):
         nbytes = numel * torch.empty(0, dtype=dtype).element_size()
         return base[off:off + nbytes].view(dtype)
 
+    if P == 0:
+        dev = state.radii.device
+        e = lambda dt, *shape: torch.empty(*shape, dtype=dt, device=dev)
+        out.update(records=e(torch.float32, 0, 12), tiles_touched=e(torch.int32, 0), clamped=e(torch.uint8, 0),
+                   depth_order=e(torch.int32, 0), point_list=e(torch.int32, 0), tile_keys=e(torch.int32, 0),
+                   final_T=e(torch.float32, H, W), n_contrib=e(torch.int32, H, W),
+                   ranges=torch.zeros(((W + 15) // 16) * ((H + 15) // 16), 2, dtype=torch.int32, device=dev))
+        return out
     gv = _lib.GeometryView()
     _lib.check(lib.gsr_view_geometry(_ptr(state.geom), P, C.byref(gv)), "gsr_view_geometry")
     out["records"] = view(gv.records, state.geom, P * 12, torch.float32).view(P, 12)

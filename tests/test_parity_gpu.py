@@ -73,10 +73,10 @@ def test_forward_matches_reference_cuda_bit_exact(fwd_variant):
             assert torch.equal(rec[:, 6], s["depths"][vis]), name
             assert torch.equal(rec[:, 8:11], s["rgb"][vis]), name
     finally:
-        _lib.set_option("render_fwd_variant", 2)
+        _lib.set_option("render_fwd_variant", 3)
 
 
-@pytest.mark.parametrize("bwd_variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("bwd_variant", [0, 1, 2, 3, 4, 5, 6, 7])
 def test_backward_matches_reference_cuda(bwd_variant):
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
@@ -97,7 +97,7 @@ def test_backward_matches_reference_cuda(bwd_variant):
                 assert err <= 1e-4 + 10 * noise, (name, a, err, noise)
                 assert np.abs(g - r).max() <= 1e-3 * np.abs(r).max() + 1e-12, (name, a)
     finally:
-        _lib.set_option("render_bwd_variant", 2)
+        _lib.set_option("render_bwd_variant", 4)
 
 
 def test_forward_backward_vs_cpu_oracle():
@@ -224,3 +224,35 @@ def test_full_size_properties_config3():
     out2 = run_ours(cloud, cam, (0, 0, 0), dL=2.0 * dL)
     a, b = out["grads"]["dmean3D"], out2["grads"]["dmean3D"]
     assert rel_l2((2 * a).cpu().numpy(), b.cpu().numpy()) <= 1e-4
+
+
+def test_host_buffer_api():
+    """C-ABI host-buffer entry points (gsr_host_*): same images as the tensor path, checksums of all gradients."""
+    import ctypes as C
+    lib = _lib.load()
+    cloud, _ = synth.make_config("c3", P=50_000)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 320, 240, 61.0)[4]
+    dL = np.random.default_rng(2).uniform(size=(3, 240, 320)).astype(np.float32)
+    ref = run_ours(cloud, cam, (0.2, 0.3, 0.4), dL=dL)
+    ctx = C.c_void_p(lib.gsr_host_create())
+    assert ctx.value
+    P, M = cloud.means3D.shape[0], cloud.shs.shape[1]
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    arrs = [np.ascontiguousarray(x, np.float32) for x in (cloud.means3D, cloud.opacities, cloud.shs, cloud.scales, cloud.rotations)]
+    _lib.check(lib.gsr_host_upload_cloud(ctx, P, M, *[p(a) for a in arrs]), "upload")
+    bg = np.array([0.2, 0.3, 0.4], np.float32)
+    s = _lib.Settings(240, 320, cam.tanfovx, cam.tanfovy, 1.0, 3, M, 0, 0, p(bg).value, p(cam.viewmatrix).value,
+                      p(cam.projmatrix).value, p(cam.campos).value)
+    color = np.zeros((3, 240, 320), np.float32); radii = np.zeros(P, np.int32); sums = np.zeros(8, np.float64)
+    R = lib.gsr_host_step(ctx, C.byref(s), p(dL), p(color), p(radii), p(sums))
+    lib.gsr_host_destroy(ctx)
+    assert R == ref["R"]
+    assert np.array_equal(color, ref["color"].cpu().numpy())
+    assert np.array_equal(radii, ref["radii"].cpu().numpy())
+    g = ref["grads"]
+    want = [g["dmean3D"], g["dmean2D"], None, g["dopacity"], None, g["dsh"], g["dscale"], g["drot"]]
+    for i, w in enumerate(want):
+        if w is not None:
+            ws = float(w.double().sum())
+            scale = float(w.double().abs().sum()) + 1e-12
+            assert abs(sums[i] - ws) <= 1e-5 * scale, (i, sums[i], ws)
