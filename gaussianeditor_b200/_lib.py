@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libgsr_b200.so")
 # every symbol include/gsr_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "gsr_abi_version", "gsr_last_error", "gsr_geometry_bytes", "gsr_image_bytes", "gsr_binning_bytes",
-    "gsr_backward_scratch_bytes", "gsr_forward_preprocess", "gsr_forward_render", "gsr_backward",
+    "gsr_backward_scratch_bytes", "gsr_forward_preprocess", "gsr_forward_render",
+    "gsr_forward_render_speculative", "gsr_backward",
     "gsr_mark_visible", "gsr_apply_weights", "gsr_view_geometry", "gsr_view_binning", "gsr_view_image",
     "gsr_set_option", "gsr_get_option", "gsr_launch_count", "gsr_profile_read", "gsr_host_create", "gsr_host_destroy",
     "gsr_host_upload_cloud", "gsr_host_step",
@@ -94,6 +95,8 @@ def load():
     lib.gsr_forward_preprocess.argtypes = [C.POINTER(Settings), C.POINTER(Cloud), vp, sz, vp, vp, vp]
     lib.gsr_forward_render.restype = C.c_int
     lib.gsr_forward_render.argtypes = [C.POINTER(Settings), C.POINTER(Cloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp]
+    lib.gsr_forward_render_speculative.restype = C.c_int
+    lib.gsr_forward_render_speculative.argtypes = lib.gsr_forward_render.argtypes
     lib.gsr_backward.restype = C.c_int
     lib.gsr_backward.argtypes = [C.POINTER(Settings), C.POINTER(Cloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz,
                                  C.POINTER(Grads), vp]

@@ -135,9 +135,10 @@ static int carve_all(const gsr_settings* s, const gsr_cloud* c, int64_t R, void*
   return GSR_OK;
 }
 
-int gsr_forward_render(const gsr_settings* s, const gsr_cloud* c, int32_t R, void* geometry, size_t geometry_bytes,
-                       void* binning, size_t binning_bytes, void* image, size_t image_bytes, const int32_t* radii,
-                       float* out_color, float* out_depth, void* stream) {
+static int forward_render_impl(const gsr_settings* s, const gsr_cloud* c, int32_t R, bool speculative, void* geometry,
+                               size_t geometry_bytes, void* binning, size_t binning_bytes, void* image,
+                               size_t image_bytes, const int32_t* radii, float* out_color, float* out_depth,
+                               void* stream) {
   int rc = validate(s, c);
   if (rc) return rc;
   if (!out_color || !out_depth) { set_error("output images are null"); return GSR_ERR_INVALID; }
@@ -151,10 +152,26 @@ int gsr_forward_render(const gsr_settings* s, const gsr_cloud* c, int32_t R, voi
   GeometryWS g; BinningWS b; ImageWS im;
   rc = carve_all(s, c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, g, b, im);
   if (rc) return rc;
-  rc = run_binning(*s, *c, R, g, b, im, radii, st);
+  rc = run_binning(*s, *c, R, speculative, g, b, im, radii, st);
   if (rc) return rc;
   StageScope t(ST_RENDER_FWD, st);
   return launch_render_fwd(*s, g, b, im, out_color, out_depth, st);
+}
+
+int gsr_forward_render(const gsr_settings* s, const gsr_cloud* c, int32_t R, void* geometry, size_t geometry_bytes,
+                       void* binning, size_t binning_bytes, void* image, size_t image_bytes, const int32_t* radii,
+                       float* out_color, float* out_depth, void* stream) {
+  return forward_render_impl(s, c, R, false, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, radii,
+                             out_color, out_depth, stream);
+}
+
+int gsr_forward_render_speculative(const gsr_settings* s, const gsr_cloud* c, int32_t capacity, void* geometry,
+                                   size_t geometry_bytes, void* binning, size_t binning_bytes, void* image,
+                                   size_t image_bytes, const int32_t* radii, float* out_color, float* out_depth,
+                                   void* stream) {
+  if (capacity <= 0) { set_error("speculative capacity must be positive"); return GSR_ERR_INVALID; }
+  return forward_render_impl(s, c, capacity, true, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes,
+                             radii, out_color, out_depth, stream);
 }
 
 int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
@@ -210,7 +227,7 @@ int gsr_apply_weights(const gsr_settings* s, const gsr_cloud* c, int32_t R, void
   GeometryWS g; BinningWS b; ImageWS im;
   rc = carve_all(s, c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, g, b, im);
   if (rc) return rc;
-  rc = run_binning(*s, *c, R, g, b, im, radii, st);
+  rc = run_binning(*s, *c, R, false, g, b, im, radii, st);
   if (rc) return rc;
   StageScope t(ST_APPLY_W, st);
   return launch_apply_weights(*s, g, b, im, image_weights, CH, weights, cnt, st);

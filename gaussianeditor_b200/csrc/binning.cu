@@ -61,14 +61,21 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
 constexpr int EMIT_THREADS = 256;
 template <typename KeyT>
 __global__ void __launch_bounds__(EMIT_THREADS)
-emit_instances_kernel(int P, uint32_t R, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
+emit_instances_kernel(int P, uint32_t cap, const uint32_t* __restrict__ R_dev, KeyT pad_key,
+                      const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                       const uint32_t* __restrict__ tiles_touched, const SplatRecord* __restrict__ records,
                       const int32_t* __restrict__ radii, int gx, int gy, KeyT* __restrict__ keys,
                       uint32_t* __restrict__ vals) {
   const unsigned F = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const uint32_t s0 = (blockIdx.x * EMIT_THREADS + threadIdx.x) - lane;  // first slot of this warp
-  if (s0 >= R) return;
+  // Speculative launches size the grid for a capacity `cap` >= R that the host guessed before R was known; R itself is
+  // read from the scan result on the device and the slots [R, cap) get a key that sorts behind every tile.
+  const uint32_t R = R_dev ? min(__ldg(R_dev), cap) : cap;
+  if (s0 >= R) {
+    if (s0 + lane < cap) { keys[s0 + lane] = pad_key; vals[s0 + lane] = 0u; }
+    return;
+  }
   // smallest rank r0 with offsets[r0] > s0; invariant: answer in [lo, lo+n), offsets[lo+n-1] > s0
   int lo = 0, n = P;
   while (n > 1) {  // warp-uniform
@@ -101,13 +108,18 @@ emit_instances_kernel(int P, uint32_t R, const uint32_t* __restrict__ order, con
   if (s0 + lane < R) {
     keys[s] = (KeyT)((rmin.y + ry) * gx + (rmin.x + rx));
     vals[s] = idx;
+  } else if (s0 + lane < cap) {
+    keys[s0 + lane] = pad_key;
+    vals[s0 + lane] = 0u;
   }
 }
 
 // rasterizer_impl.cu:105-125 on 32-bit tile keys; ranges must be zeroed beforehand (:263-265)
 template <typename KeyT>
-__global__ void tile_ranges_kernel(int L, const KeyT* __restrict__ keys, uint2* __restrict__ ranges) {
+__global__ void tile_ranges_kernel(int cap, const uint32_t* __restrict__ R_dev, const KeyT* __restrict__ keys,
+                                   uint2* __restrict__ ranges) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = R_dev ? (int)min(__ldg(R_dev), (uint32_t)cap) : cap;  // padding slots [L, cap) carry no tile
   if (idx >= L) return;
   const uint32_t cur = keys[idx];
   if (idx == 0)
@@ -145,22 +157,25 @@ size_t tile_sort_temp_bytes(int64_t R) {
 }
 
 template <typename KeyT>
-int bin_typed(const gsr_cloud& c, int R, int gx, int gy, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
-              const int32_t* radii, cudaStream_t st, bool debug) {
+int bin_typed(const gsr_cloud& c, int R, bool speculative, int gx, int gy, const GeometryWS& g, const BinningWS& b,
+              const ImageWS& im, const int32_t* radii, cudaStream_t st, bool debug) {
+  const uint32_t* R_dev = speculative ? g.offsets + (c.P - 1) : nullptr;
+  const int bit = (int)higher_msb((uint32_t)(gx * gy));
+  const KeyT pad_key = (KeyT)((1u << bit) - 1u);  // > every tile id (ids <= Ntile-1 <= 2^bit - 2), inside the sorted bits
   KeyT* ku = reinterpret_cast<KeyT*>(b.keys_unsorted);
   KeyT* ks = reinterpret_cast<KeyT*>(b.keys_sorted);
   int rc;
   {
     StageScope t(ST_EMIT, st);
     emit_instances_kernel<KeyT><<<(R + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(
-        c.P, (uint32_t)R, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, ku, b.vals_unsorted);
+        c.P, (uint32_t)R, R_dev, pad_key, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, ku,
+        b.vals_unsorted);
     g_launches++;
     rc = check_launch("emit_instances", debug, st);
     if (rc) return rc;
   }
   {
     StageScope t(ST_TILE_SORT, st);
-    const int bit = (int)higher_msb((uint32_t)(gx * gy));
     size_t tb = b.cub_temp_bytes;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(b.cub_temp, tb, (const KeyT*)ku, ks, (const uint32_t*)b.vals_unsorted,
                                                     b.point_list, R, 0, bit, st);
@@ -168,7 +183,7 @@ int bin_typed(const gsr_cloud& c, int R, int gx, int gy, const GeometryWS& g, co
     if (e != cudaSuccess) return check_cuda(e, "tile sort");
   }
   StageScope t(ST_RANGES, st);
-  tile_ranges_kernel<KeyT><<<(R + 255) / 256, 256, 0, st>>>(R, ks, im.ranges);
+  tile_ranges_kernel<KeyT><<<(R + 255) / 256, 256, 0, st>>>(R, R_dev, ks, im.ranges);
   g_launches++;
   return check_launch("tile_ranges", debug, st);
 }
@@ -263,8 +278,8 @@ int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* n
   return check_launch("depth order + scan", debug, st);
 }
 
-int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, const GeometryWS& g, const BinningWS& b,
-                const ImageWS& im, const int32_t* radii, cudaStream_t st) {
+int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculative, const GeometryWS& g,
+                const BinningWS& b, const ImageWS& im, const int32_t* radii, cudaStream_t st) {
   const int W = s.image_width, H = s.image_height;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const bool debug = s.debug != 0;
@@ -273,8 +288,8 @@ int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, const Geometry
   if (R <= 0) return GSR_OK;
   // tile ids fit 16 bits for every image up to 4096x4096 (65536 tiles): half the key traffic of the sort
   if ((int64_t)gx * gy <= 65536 && g_opt.tile_key_bits == 16)
-    return bin_typed<uint16_t>(c, R, gx, gy, g, b, im, radii, st, debug);
-  return bin_typed<uint32_t>(c, R, gx, gy, g, b, im, radii, st, debug);
+    return bin_typed<uint16_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug);
+  return bin_typed<uint32_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug);
 }
 
 }  // namespace gsr

@@ -93,8 +93,8 @@ int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const Geome
                           cudaStream_t st);
 int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
                              bool debug);
-int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, const GeometryWS& g, const BinningWS& b,
-                const ImageWS& im, const int32_t* radii, cudaStream_t st);
+int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculative, const GeometryWS& g,
+                const BinningWS& b, const ImageWS& im, const int32_t* radii, cudaStream_t st);
 int launch_render_fwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
                       float* out_color, float* out_depth, cudaStream_t st);
 int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,

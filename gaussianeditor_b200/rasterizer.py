@@ -40,6 +40,8 @@ class GaussianRasterizationSettings(NamedTuple):
 
 _size_cache: dict = {}
 _pinned: dict = {}
+_r_hint: dict = {}          # (device, P, W, H) -> largest num_rendered seen recently
+SPECULATIVE = True          # launch the second forward half before num_rendered is known (see _forward_impl)
 
 
 def _f32c(t: torch.Tensor, device) -> torch.Tensor:
@@ -88,7 +90,7 @@ def _make_cloud(P, means3D, opacities, sh, colors_precomp, scales, rotations, co
 
 class _ForwardState:
     """What the forward leaves behind for backward / apply_weights / parity tests."""
-    __slots__ = ("geom", "binning", "img", "radii", "num_rendered", "P", "M", "W", "H")
+    __slots__ = ("geom", "binning", "img", "radii", "num_rendered", "cap", "P", "M", "W", "H")
 
 
 def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, *, render=True):
@@ -120,20 +122,45 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         pinned = _pinned_i32(device)
         _lib.check(lib.gsr_forward_preprocess(C.byref(s), C.byref(c), _ptr(state.geom), gbytes, _ptr(state.radii),
                                               C.c_void_p(pinned.data_ptr()), st), "gsr_forward_preprocess")
-        stream.synchronize()
-        R = int(pinned[0])
-        state.num_rendered = R
-        bbytes = lib.gsr_binning_bytes(P, R, W, H) if R > 0 else 0
         ibytes = lib.gsr_image_bytes(W, H)
-        state.binning = torch.empty(bbytes, **u8)
         state.img = torch.empty(ibytes, **u8)
         color = depth = None
         if render:
             color = torch.empty(3, H, W, dtype=torch.float32, device=device)
             depth = torch.empty(1, H, W, dtype=torch.float32, device=device)
-            _lib.check(lib.gsr_forward_render(C.byref(s), C.byref(c), R, _ptr(state.geom), gbytes,
-                                              _ptr(state.binning), bbytes, _ptr(state.img), ibytes,
-                                              _ptr(state.radii), _ptr(color), _ptr(depth), st), "gsr_forward_render")
+        key = (device.index, P, W, H)
+        hint = _r_hint.get(key)
+        done = False
+        if SPECULATIVE and render and P > 0 and hint:
+            # The count of (Gaussian, tile) instances is only known on the device at this point. Instead of idling
+            # the GPU while the host fetches it (the reference blocks in cudaMemcpy), enqueue the second half now for
+            # a guessed capacity, THEN wait for the count: the GPU keeps working while the host waits. A wrong guess
+            # (count > capacity) is detected below and the second half is redone with the exact size.
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            cap = int(hint * 1.25) + 4096
+            bbytes = lib.gsr_binning_bytes(P, cap, W, H)
+            state.binning = torch.empty(bbytes, **u8)
+            _lib.check(lib.gsr_forward_render_speculative(C.byref(s), C.byref(c), cap, _ptr(state.geom), gbytes,
+                                                          _ptr(state.binning), bbytes, _ptr(state.img), ibytes,
+                                                          _ptr(state.radii), _ptr(color), _ptr(depth), st),
+                       "gsr_forward_render_speculative")
+            ev.synchronize()
+            R = int(pinned[0])
+            if R <= cap:
+                state.num_rendered, state.cap, done = R, cap, True
+        if not done:
+            stream.synchronize()
+            R = int(pinned[0])
+            state.num_rendered = state.cap = R
+            bbytes = lib.gsr_binning_bytes(P, R, W, H) if R > 0 else 0
+            state.binning = torch.empty(bbytes, **u8)
+            if render:
+                _lib.check(lib.gsr_forward_render(C.byref(s), C.byref(c), R, _ptr(state.geom), gbytes,
+                                                  _ptr(state.binning), bbytes, _ptr(state.img), ibytes,
+                                                  _ptr(state.radii), _ptr(color), _ptr(depth), st), "gsr_forward_render")
+        if P > 0:
+            _r_hint[key] = max(R, int(0.9 * _r_hint.get(key, 0)))
     inputs = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
     return color, depth, state, inputs
 
@@ -182,7 +209,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 gr = _lib.Grads(_ptr(dL_dmeans3D), _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity),
                                 _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
                 st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-                _lib.check(lib.gsr_backward(C.byref(s), C.byref(c), state.num_rendered, _ptr(geom), geom.numel(),
+                _lib.check(lib.gsr_backward(C.byref(s), C.byref(c), state.cap, _ptr(geom), geom.numel(),
                                             _ptr(binning), binning.numel(), _ptr(img), img.numel(), _ptr(radii),
                                             _ptr(grad_out_color), _ptr(scratch), sbytes, C.byref(gr), st),
                            "gsr_backward")
@@ -286,6 +313,7 @@ def forward_state_views(state: _ForwardState):
     """Decode the opaque workspaces of a forward into torch tensors (views onto the workspace memory)."""
     lib = _lib.load()
     P, R, W, H = state.P, state.num_rendered, state.W, state.H
+    cap = state.cap
     out = {}
 
     def view(ptr, base: torch.Tensor, numel, dtype):
@@ -315,7 +343,7 @@ def forward_state_views(state: _ForwardState):
     out["ranges"] = view(iv.ranges, state.img, ntile * 2, torch.int32).view(ntile, 2)
     if R > 0:
         bv = _lib.BinningView()
-        _lib.check(lib.gsr_view_binning(_ptr(state.binning), P, R, W, H, C.byref(bv)), "gsr_view_binning")
+        _lib.check(lib.gsr_view_binning(_ptr(state.binning), P, cap, W, H, C.byref(bv)), "gsr_view_binning")
         out["point_list"] = view(bv.point_list, state.binning, R, torch.int32)
         out["tile_keys"] = view(bv.tile_keys, state.binning, R, torch.int16 if bv.tile_key_bytes == 2 else torch.int32)
     else:

@@ -116,6 +116,19 @@ GSR_API int gsr_forward_render(const gsr_settings* s, const gsr_cloud* c, int32_
                        size_t geometry_bytes, void* binning, size_t binning_bytes, void* image, size_t image_bytes,
                        const int32_t* radii, float* out_color, float* out_depth, void* stream);
 
+/* ---- forward, second half, without waiting for num_rendered ------------------------------------------------
+ * Same as gsr_forward_render, but launched BEFORE the host knows num_rendered: `capacity` is the caller's guess
+ * (e.g. 1.25x the previous frame's value) and sizes the binning workspace and the launches; the real count is read
+ * from the scan result on the device and the slots [num_rendered, capacity) are padding that sorts behind every
+ * tile. The caller must afterwards read *num_rendered_host (after the stream reaches the copy issued by
+ * gsr_forward_preprocess) and, if it exceeds `capacity`, discard the outputs and call gsr_forward_render with the
+ * exact count. gsr_backward then takes `capacity` as its num_rendered argument (it only sizes the workspace).
+ * This keeps the GPU busy while the host waits for the count (the reference blocks in cudaMemcpy with an idle
+ * GPU, rasterizer_impl.cu:237). */
+GSR_API int gsr_forward_render_speculative(const gsr_settings* s, const gsr_cloud* c, int32_t capacity, void* geometry,
+                       size_t geometry_bytes, void* binning, size_t binning_bytes, void* image, size_t image_bytes,
+                       const int32_t* radii, float* out_color, float* out_depth, void* stream);
+
 /* ---- backward ------------------------------------------------------------------------------------------
  * dL_dout_color [3,H,W]; the three workspaces and `radii` are the ones the forward produced. */
 GSR_API int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t num_rendered, const void* geometry,

@@ -256,3 +256,32 @@ def test_host_buffer_api():
             ws = float(w.double().sum())
             scale = float(w.double().abs().sum()) + 1e-12
             assert abs(sums[i] - ws) <= 1e-5 * scale, (i, sums[i], ws)
+
+
+def test_speculative_second_half_equals_exact_path():
+    """The sync-free forward (capacity guessed from the previous frame) must give the same bits as the exact path,
+    including when the guess is too small and the second half is redone."""
+    import gaussianeditor_b200.rasterizer as RZ
+    cloud, _ = synth.make_config("c3", P=40_000)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 320, 240, 61.0)[6]
+    dL = np.random.default_rng(9).uniform(size=(3, 240, 320)).astype(np.float32)
+    key = (0, cloud.means3D.shape[0], 320, 240)
+    try:
+        RZ.SPECULATIVE = False
+        exact = run_ours(cloud, cam, (0.5, 0.5, 0.5), dL=dL)
+        RZ.SPECULATIVE = True
+        RZ._r_hint[key] = exact["R"]            # good guess -> speculative path
+        spec = run_ours(cloud, cam, (0.5, 0.5, 0.5), dL=dL)
+        assert spec["state"].cap > spec["R"] == exact["R"]
+        RZ._r_hint[key] = 10                    # hopeless guess -> overflow -> redo with the exact size
+        redo = run_ours(cloud, cam, (0.5, 0.5, 0.5), dL=dL)
+        assert redo["state"].cap == redo["R"] == exact["R"]
+        for other in (spec, redo):
+            assert torch.equal(other["color"], exact["color"]) and torch.equal(other["depth"], exact["depth"])
+            assert torch.equal(other["views"]["point_list"], exact["views"]["point_list"])
+            assert torch.equal(other["views"]["ranges"], exact["views"]["ranges"])
+            assert torch.equal(other["views"]["n_contrib"], exact["views"]["n_contrib"])
+            for k in ("dmean3D", "dsh", "dopacity"):
+                assert rel_l2(other["grads"][k].cpu().numpy(), exact["grads"][k].cpu().numpy()) <= 1e-5
+    finally:
+        RZ.SPECULATIVE = True
