@@ -43,7 +43,7 @@ struct BwdArgs {
 // backward.cu:515), `bgT` = T_final * (bg . dL_dpixel).
 //
 // The nine sums of backward.cu:523-554 are accumulated as moments of w = dL_dG * G over the pixels,
-//   g[3..8] = sum w*{1, dx, dy, dx*dx, dx*dy, dy*dy},   g[0..2] = sum alpha*T*dL_dpixel,
+//   g[3..7] = sum w*{dx, dy, dx*dx, dx*dy, dy*dy},  g[8] = sum w,  g[0..2] = sum alpha*T*dL_dpixel,
 // and turned into the reference's quantities once per (tile, splat) by finish_sums() -- the per-splat factors
 // (conic, opacity, 0.5*W, 0.5*H) are constant over the pixels, so this is the same sum with the common factor
 // pulled out (8 instead of 17 operations per hit).
@@ -72,36 +72,43 @@ __device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, floa
   dL_dalpha = fmaf(dL_dalpha, p.T, -p.bgT * rcp);
   const float w = (o * dL_dalpha) * G;  // dL_dG * G
   const float wdx = w * dx, wdy = w * dy;
-  g[3] += w;
-  g[4] += wdx;
-  g[5] += wdy;
-  g[6] = fmaf(wdx, dx, g[6]);
-  g[7] = fmaf(wdx, dy, g[7]);
-  g[8] = fmaf(wdy, dy, g[8]);
+  g[3] += wdx;
+  g[4] += wdy;
+  g[5] = fmaf(wdx, dx, g[5]);
+  g[6] = fmaf(wdx, dy, g[6]);
+  g[7] = fmaf(wdy, dy, g[7]);
+  g[8] += w;
 }
 
-// Warp totals of the moments -> the reference's nine gradient contributions, for the lane that owns output j
-// (acc layout: 0..2 dcolor, 3..4 dmean2D, 5..7 dconic a,b,c, 8 dopacity). `tot` is the total of moment (lane>>2)
-// on lanes 0,4,..,28 and m8 = sum w*dy*dy on every lane; the other moments are fetched with shuffles.
-__device__ __forceinline__ void finish_and_add(float* dst, float tot, float m8, int lane, float A, float B, float C,
-                                               float o, float ddelx_dx, float ddely_dy) {
-  const unsigned F = 0xffffffffu;
-  const float s_w = __shfl_sync(F, tot, 12);   // moment 3: sum w
-  const float s_x = __shfl_sync(F, tot, 16);   // moment 4: sum w*dx
-  const float s_y = __shfl_sync(F, tot, 20);   // moment 5: sum w*dy
-  const float s_xx = __shfl_sync(F, tot, 24);  // moment 6
-  const float s_xy = __shfl_sync(F, tot, 28);  // moment 7
-  float v;
-  switch (lane >> 2) {
-    case 0: case 1: case 2: v = tot; break;                          // dL/dcolor
-    case 3: v = -(s_x * A + s_y * B) * ddelx_dx; break;             // dL/dmean2D.x = sum dL_dG*dG_ddelx*0.5W
-    case 4: v = -(s_y * C + s_x * B) * ddely_dy; break;             // dL/dmean2D.y
-    case 5: v = -0.5f * s_xx; break;                                 // dL/dconic.a
-    case 6: v = -0.5f * s_xy; break;                                 // dL/dconic.b
-    default: v = -0.5f * m8; break;                                  // dL/dconic.c
-  }
-  if ((lane & 3) == 0) atomicAdd(dst + (lane >> 2), v);
-  if (lane == 1) atomicAdd(dst + 8, __fdividef(s_w, o));             // dL/dopacity = sum G*dL_dalpha = sum w / o
+// Warp totals of the moments -> the reference's nine gradient contributions (acc layout: 0..2 dcolor, 3..4 dmean2D,
+// 5..7 dconic a,b,c, 8 dopacity). After warp_sum9 lane 4*j holds the total of moment j (j = 0..7) and every lane holds
+// sw = sum w. Output j is a two-term combination  ka*tot + kb*other  with `other` = the partner moment of the
+// (w*dx, w*dy) pair (lanes 12..15 <-> 16..19, one shuffle) and lane-constant selectors -- no divergent code:
+//   j<3: tot | j=3: -(A*s_x + B*s_y)*0.5W | j=4: -(C*s_y + B*s_x)*0.5H | j=5..7: -0.5*tot | opacity: sw / o
+struct LaneRole {
+  bool is_x, is_y, writer, opac;  // moment-3 group, moment-4 group, lane that issues the atomic, opacity lane
+  float kconst;                   // 1 for the colour groups, -0.5 for the conic groups
+  int slot;
+};
+__device__ __forceinline__ LaneRole lane_role(int lane) {
+  LaneRole r;
+  r.slot = lane >> 2;
+  r.is_x = r.slot == 3;
+  r.is_y = r.slot == 4;
+  r.writer = (lane & 3) == 0;
+  r.opac = lane == 1;
+  r.kconst = r.slot < 3 ? 1.0f : -0.5f;
+  return r;
+}
+__device__ __forceinline__ void finish_and_add(float* dst, float tot, float sw, const LaneRole& role, float A, float B,
+                                               float C, float o, float ddelx_dx, float ddely_dy) {
+  const float other = __shfl_xor_sync(0xffffffffu, tot, 28);  // s_x <-> s_y between lanes 12..15 and 16..19
+  const float nBx = -B * ddelx_dx, nBy = -B * ddely_dy;
+  const float ka = role.is_x ? -A * ddelx_dx : (role.is_y ? -C * ddely_dy : role.kconst);
+  const float kb = role.is_x ? nBx : (role.is_y ? nBy : 0.0f);
+  const float v = fmaf(kb, other, ka * tot);
+  if (role.writer) atomicAdd(dst + role.slot, v);
+  if (role.opac) atomicAdd(dst + 8, __fdividef(sw, o));  // dL/dopacity = sum G*dL_dalpha = (sum w) / o
 }
 
 // Sum nine per-lane values over the warp. g[0..7] go through a transposing butterfly: after it, lane 4*j (and
@@ -169,6 +176,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
   const size_t HW = (size_t)a.H * a.W;
   const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+  const LaneRole role = lane_role(lane);
 
   PixState ps[NSB];
   uint32_t nc[NSB], sblast[NSB];
@@ -266,7 +274,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
       if (__any_sync(0xffffffffu, any)) {
         float m8;
         const float tot = warp_sum9(g, lane, m8);
-        finish_and_add(a.acc + (size_t)sid[j] * ACC_STRIDE, tot, m8, lane, s0.z, s0.w, s1.x, s1.y, ddelx_dx, ddely_dy);
+        finish_and_add(a.acc + (size_t)sid[j] * ACC_STRIDE, tot, m8, role, s0.z, s0.w, s1.x, s1.y, ddelx_dx, ddely_dy);
       }
     }
     __syncwarp();
@@ -308,6 +316,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
   const size_t HW = (size_t)a.H * a.W;
   const float bg0 = a.bg[0], bg1 = a.bg[1], bg2 = a.bg[2];
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+  const LaneRole role = lane_role(lane);
 
   PixState ps[NSB];
   uint32_t nc[NSB], sblast[NSB];
@@ -384,23 +393,30 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
         t0[r] = __fmul_rn(__fmul_rn(dyv[r], s1.x), dyv[r]);
       }
       // ---- NSB independent evaluations ----
-      float G[NSB], al[NSB];
-      bool anyhit = false;
+      float G[NSB], al[NSB], pw[NSB];
+      bool near = false;
 #pragma unroll
       for (int k = 0; k < NSB; k++) {
         const int c = k & 1, r = k >> 1;
         const float s = __fmaf_rn(dxv[c], dxA[c], t0[r]);
-        const float power = __fmaf_rn(s, -0.5f, -__fmul_rn(dxB[c], dyv[r]));
-        bool ok = ((m >> k) & 1u) && !(power > 0.0f) && spos <= nc[k];
-        float Gf = ex2_approx(power * 1.4426950408889634f);
-        float af = fminf(0.99f, s1.y * Gf);
-        if (ok && fabsf(af - 1.0f / 255.0f) <= (1.0f / 255.0f) * 1e-5f) {  // too close to call: the forward's arithmetic
-          Gf = expf(power);
-          af = fminf(0.99f, __fmul_rn(s1.y, Gf));
+        pw[k] = __fmaf_rn(s, -0.5f, -__fmul_rn(dxB[c], dyv[r]));
+        G[k] = ex2_approx(pw[k] * 1.4426950408889634f);
+        al[k] = fminf(0.99f, s1.y * G[k]);
+        near |= fabsf(al[k] - 1.0f / 255.0f) <= (1.0f / 255.0f) * 1e-5f;
+      }
+      if (near) {  // rare: too close to the 1/255 threshold to call with ex2.approx -> the forward's exact arithmetic
+#pragma unroll
+        for (int k = 0; k < NSB; k++) {
+          G[k] = expf(pw[k]);
+          al[k] = fminf(0.99f, __fmul_rn(s1.y, G[k]));
         }
-        ok = ok && !(af < 1.0f / 255.0f);
-        G[k] = ok ? Gf : 0.f;
-        al[k] = ok ? af : 0.f;
+      }
+      bool anyhit = false;
+#pragma unroll
+      for (int k = 0; k < NSB; k++) {
+        const bool ok = ((m >> k) & 1u) && !(pw[k] > 0.0f) && spos <= nc[k] && !(al[k] < 1.0f / 255.0f);
+        G[k] = ok ? G[k] : 0.f;
+        al[k] = ok ? al[k] : 0.f;
         anyhit |= ok;
       }
       if (!__any_sync(0xffffffffu, anyhit)) continue;
@@ -414,7 +430,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
       }
       float m8;
       const float tot = warp_sum9(g, lane, m8);
-      finish_and_add(a.acc + (size_t)sid[j] * ACC_STRIDE, tot, m8, lane, s0.z, s0.w, s1.x, s1.y, ddelx_dx, ddely_dy);
+      finish_and_add(a.acc + (size_t)sid[j] * ACC_STRIDE, tot, m8, role, s0.z, s0.w, s1.x, s1.y, ddelx_dx, ddely_dy);
     }
     __syncwarp();
   }
@@ -448,6 +464,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs 
     nc = a.n_contrib[pix_id];
   }
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
+  const LaneRole role = lane_role(lane);
 
   for (int hi = tl; hi > 0; hi -= TILE_PIX) {
     __syncthreads();
@@ -481,7 +498,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs 
       if (__any_sync(0xffffffffu, hit)) {
         float m8;
         const float tot = warp_sum9(g, lane, m8);
-        finish_and_add(a.acc + (size_t)s_ids[j] * ACC_STRIDE, tot, m8, lane, q0.z, q0.w, q1.x, q1.y, ddelx_dx, ddely_dy);
+        finish_and_add(a.acc + (size_t)s_ids[j] * ACC_STRIDE, tot, m8, role, q0.z, q0.w, q1.x, q1.y, ddelx_dx, ddely_dy);
       }
     }
   }

@@ -47,7 +47,7 @@ def _small_cases():
             ("c3odd", c3, cam_odd, (0.2, 0.5, 0.7))]
 
 
-@pytest.mark.parametrize("fwd_variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("fwd_variant", [0, 1, 2, 3, 4])
 def test_forward_matches_reference_cuda_bit_exact(fwd_variant):
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
