@@ -393,8 +393,16 @@ def main():
         dom = max(stages, key=stages.get)
         peak, peak_src = measured_peaks()
         ach = ab[dom] / (stages[dom] * 1e-3) / 1e9
+        traffic = None
+        try:  # DRAM bytes per launch from the committed ncu --set full capture of the same command
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f)["kernels"][dom]["dram_bytes"]
+        except Exception:
+            pass
         line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                            "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                            "note": "the render kernels are FP32-issue bound, not HBM bound (DESIGN.md section 5): "
+                                    "frac is the share of the HBM time the algorithmic bytes would need",
                             "alg_bytes": ab[dom], "kernel_ms": stages[dom],
                             "all": {k: {"ms": round(stages[k], 4), "alg_GB": round(ab[k] / 1e9, 4),
                                         "GBps": round(ab[k] / (stages[k] * 1e-3) / 1e9, 1),

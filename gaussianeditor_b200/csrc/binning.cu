@@ -15,6 +15,9 @@
 // Equality of point_list / ranges / R with the reference is asserted bit-for-bit in the GPU tests.
 #include <cub/cub.cuh>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace gsr {
@@ -114,46 +117,86 @@ emit_instances_kernel(int P, uint32_t cap, const uint32_t* __restrict__ R_dev, K
   }
 }
 
-// rasterizer_impl.cu:105-125 on 32-bit tile keys; ranges must be zeroed beforehand (:263-265)
+// rasterizer_impl.cu:105-125 on 16/32-bit tile keys; ranges must be zeroed beforehand (:263-265). Each thread owns
+// RANGE_ITEMS consecutive keys (one 128-bit load for 16-bit keys) plus its left neighbour.
+constexpr int RANGE_ITEMS = 8;
 template <typename KeyT>
 __global__ void tile_ranges_kernel(int cap, const uint32_t* __restrict__ R_dev, const KeyT* __restrict__ keys,
                                    uint2* __restrict__ ranges) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int L = R_dev ? (int)min(__ldg(R_dev), (uint32_t)cap) : cap;  // padding slots [L, cap) carry no tile
-  if (idx >= L) return;
-  const uint32_t cur = keys[idx];
-  if (idx == 0)
-    ranges[cur].x = 0;
-  else {
-    const uint32_t prev = keys[idx - 1];
-    if (cur != prev) {
-      ranges[prev].y = idx;
-      ranges[cur].x = idx;
+  const int base = (blockIdx.x * blockDim.x + threadIdx.x) * RANGE_ITEMS;
+  if (base >= L) return;
+  KeyT k[RANGE_ITEMS];
+  if (sizeof(KeyT) == 2 && base + RANGE_ITEMS <= cap) {  // workspace arrays are 256-byte aligned, base*2 is 16-byte aligned
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(keys + base));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < RANGE_ITEMS; i++) k[i] = (KeyT)((w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu);
+  } else {
+#pragma unroll
+    for (int i = 0; i < RANGE_ITEMS; i++) k[i] = base + i < L ? keys[base + i] : (KeyT)0;
+  }
+  uint32_t prev = base > 0 ? (uint32_t)keys[base - 1] : 0u;
+#pragma unroll
+  for (int i = 0; i < RANGE_ITEMS; i++) {
+    const int idx = base + i;
+    if (idx < L) {
+      const uint32_t cur = (uint32_t)k[i];
+      if (idx == 0)
+        ranges[cur].x = 0;
+      else if (cur != prev) {
+        ranges[prev].y = idx;
+        ranges[cur].x = idx;
+      }
+      if (idx == L - 1) ranges[cur].y = L;
+      prev = cur;
     }
   }
-  if (idx == L - 1) ranges[cur].y = L;
 }
 
+// CUB's temp-size queries depend only on the item count but cost several runtime calls each; every C-ABI entry point
+// re-derives the workspace layout, so they are memoised (single-threaded callers per the ABI; a mutex keeps it safe).
+struct SizeCache {
+  std::mutex mu;
+  std::unordered_map<long long, size_t> m;
+  template <typename Fn> size_t get(int kind, long long n, Fn fn) {
+    std::lock_guard<std::mutex> lk(mu);
+    const long long key = n * 4 + kind;
+    auto it = m.find(key);
+    if (it != m.end()) return it->second;
+    const size_t v = fn();
+    if (cudaPeekAtLastError() == cudaSuccess) m[key] = v;
+    return v;
+  }
+};
+SizeCache g_sizes;
+
 size_t depth_sort_temp_bytes(int P) {
-  size_t n = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, P);
-  return n;
+  return g_sizes.get(0, P, [&] {
+    size_t n = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, P);
+    return n;
+  });
 }
 size_t scan_temp_bytes(int P) {
-  size_t n = 0;
-  cub::TransformInputIterator<uint32_t, GatherTilesOp, cub::CountingInputIterator<uint32_t>> it(
-      cub::CountingInputIterator<uint32_t>(0), GatherTilesOp{nullptr, nullptr});
-  cub::DeviceScan::InclusiveSum(nullptr, n, it, (uint32_t*)nullptr, P);
-  return n;
+  return g_sizes.get(1, P, [&] {
+    size_t n = 0;
+    cub::TransformInputIterator<uint32_t, GatherTilesOp, cub::CountingInputIterator<uint32_t>> it(
+        cub::CountingInputIterator<uint32_t>(0), GatherTilesOp{nullptr, nullptr});
+    cub::DeviceScan::InclusiveSum(nullptr, n, it, (uint32_t*)nullptr, P);
+    return n;
+  });
 }
 size_t tile_sort_temp_bytes(int64_t R) {
-  size_t n = 0, m = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)R, 0, 32);
-  cub::DeviceRadixSort::SortPairs(nullptr, m, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)R, 0, 16);
-  return n > m ? n : m;
+  return g_sizes.get(2, R, [&] {
+    size_t n = 0, m = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)R, 0, 32);
+    cub::DeviceRadixSort::SortPairs(nullptr, m, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)R, 0, 16);
+    return n > m ? n : m;
+  });
 }
 
 template <typename KeyT>
@@ -183,7 +226,7 @@ int bin_typed(const gsr_cloud& c, int R, bool speculative, int gx, int gy, const
     if (e != cudaSuccess) return check_cuda(e, "tile sort");
   }
   StageScope t(ST_RANGES, st);
-  tile_ranges_kernel<KeyT><<<(R + 255) / 256, 256, 0, st>>>(R, R_dev, ks, im.ranges);
+  tile_ranges_kernel<KeyT><<<(R + 256 * RANGE_ITEMS - 1) / (256 * RANGE_ITEMS), 256, 0, st>>>(R, R_dev, ks, im.ranges);
   g_launches++;
   return check_launch("tile_ranges", debug, st);
 }

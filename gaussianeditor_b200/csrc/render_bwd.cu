@@ -39,8 +39,8 @@ struct BwdArgs {
   float* acc;  // [P, ACC_STRIDE]
 };
 
-// One (pixel, splat) hit. `ar*` is the reference's accum_rec updated eagerly (same operands, same order as
-// backward.cu:515), `bgT` = T_final * (bg . dL_dpixel).
+// One (pixel, splat) hit. `ar` tracks the reference's accum_rec (backward.cu:515) dotted with dL_dpixel, updated
+// eagerly; `bgT` = T_final * (bg . dL_dpixel).
 //
 // The nine sums of backward.cu:523-554 are accumulated as moments of w = dL_dG * G over the pixels,
 //   g[3..7] = sum w*{dx, dy, dx*dx, dx*dy, dy*dy},  g[8] = sum w,  g[0..2] = sum alpha*T*dL_dpixel,
@@ -48,7 +48,7 @@ struct BwdArgs {
 // (conic, opacity, 0.5*W, 0.5*H) are constant over the pixels, so this is the same sum with the common factor
 // pulled out (8 instead of 17 operations per hit).
 struct PixState {
-  float T, ar0, ar1, ar2, d0, d1, d2, bgT;
+  float T, ar, d0, d1, d2, bgT;   // ar = accum_rec . dL_dpixel (scalar; see hit_update)
 };
 
 __device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, float dy, float G, float alpha, float o,
@@ -59,16 +59,16 @@ __device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, floa
   rcp = alpha > 0.f ? rcp : 1.0f;          // (alpha, G) = (0, 0) encodes "no hit" in the branch-light variants: exact no-op
   p.T = p.T * rcp;                         // T / (1 - alpha)
   const float dchannel_dcolor = alpha * p.T;
-  const float e0 = c0 - p.ar0, e1 = c1 - p.ar1, e2 = c2 - p.ar2;
-  float dL_dalpha = e0 * p.d0;
-  dL_dalpha = fmaf(e1, p.d1, dL_dalpha);
-  dL_dalpha = fmaf(e2, p.d2, dL_dalpha);
+  // backward.cu:515-519 keeps the blended colour behind the splat per channel (accum_rec) and forms
+  // sum_ch (c_ch - accum_rec_ch) * dL_dpixel_ch. Only that dot product is ever used, and the recurrence
+  // accum_rec' = alpha*c + (1-alpha)*accum_rec is linear, so the scalar ar = accum_rec . dL_dpixel obeys
+  // ar' = ar + alpha*(c.dL_dpixel - ar): one state variable and 5 operations instead of three and 9.
+  const float s = fmaf(c2, p.d2, fmaf(c1, p.d1, c0 * p.d0));
+  float dL_dalpha = s - p.ar;
   g[0] = fmaf(dchannel_dcolor, p.d0, g[0]);
   g[1] = fmaf(dchannel_dcolor, p.d1, g[1]);
   g[2] = fmaf(dchannel_dcolor, p.d2, g[2]);
-  p.ar0 = fmaf(alpha, e0, p.ar0);          // alpha*c + (1-alpha)*accum_rec, written as accum_rec + alpha*(c - accum_rec)
-  p.ar1 = fmaf(alpha, e1, p.ar1);
-  p.ar2 = fmaf(alpha, e2, p.ar2);
+  p.ar = fmaf(alpha, dL_dalpha, p.ar);
   dL_dalpha = fmaf(dL_dalpha, p.T, -p.bgT * rcp);
   const float w = (o * dL_dalpha) * G;  // dL_dG * G
   const float wdx = w * dx, wdy = w * dy;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
     const int kg = part * NSB + k;
     const int px = tx * TILE + 8 * (kg & 1) + lx, py = ty * TILE + 4 * (kg >> 1) + ly;
     PixState p;
-    p.T = 0.f; p.ar0 = p.ar1 = p.ar2 = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
+    p.T = 0.f; p.ar = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
     nc[k] = 0;
     if (px < a.W && py < a.H) {
       const size_t pix_id = (size_t)a.W * py + px;
@@ -295,7 +295,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int NSB, int MINB>
+template <int NSB, int MINB, bool SKIP = false>
 __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(const BwdArgs a, const int ntiles) {
   __shared__ float4 s_stage[BW_WARPS][3][32];
   __shared__ uint32_t s_id[BW_WARPS][32];
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
     const int kg = part * NSB + k;
     const int px = tx * TILE + 8 * (kg & 1) + lx, py = ty * TILE + 4 * (kg >> 1) + ly;
     PixState p;
-    p.T = 0.f; p.ar0 = p.ar1 = p.ar2 = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
+    p.T = 0.f; p.ar = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
     nc[k] = 0;
     if (px < a.W && py < a.H) {
       const size_t pix_id = (size_t)a.W * py + px;
@@ -412,20 +412,23 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
         }
       }
       bool anyhit = false;
+      uint32_t hitk = 0;  // SKIP: warp-uniform mask of sub-blocks with at least one hit
 #pragma unroll
       for (int k = 0; k < NSB; k++) {
         const bool ok = ((m >> k) & 1u) && !(pw[k] > 0.0f) && spos <= nc[k] && !(al[k] < 1.0f / 255.0f);
         G[k] = ok ? G[k] : 0.f;
         al[k] = ok ? al[k] : 0.f;
         anyhit |= ok;
+        if (SKIP && __any_sync(0xffffffffu, ok)) hitk |= 1u << k;
       }
-      if (!__any_sync(0xffffffffu, anyhit)) continue;
+      if (SKIP ? hitk == 0 : !__any_sync(0xffffffffu, anyhit)) continue;
       float g[9];
 #pragma unroll
       for (int i = 0; i < 9; i++) g[i] = 0.f;
 #pragma unroll
       for (int k = 0; k < NSB; k++) {
         // (alpha, G) = (0, 0) makes every update below an exact no-op: 1/(1-0) = 1, +0 contributions
+        if (SKIP && !((hitk >> k) & 1u)) continue;
         hit_update(ps[k], g, dxv[k & 1], dyv[k >> 1], G[k], al[k], s1.y, s2.x, s2.y, s2.z);
       }
       float m8;
@@ -454,7 +457,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs 
   const size_t HW = (size_t)a.H * a.W;
 
   PixState p;
-  p.T = 0.f; p.ar0 = p.ar1 = p.ar2 = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
+  p.T = 0.f; p.ar = 0.f; p.d0 = p.d1 = p.d2 = 0.f; p.bgT = 0.f;
   uint32_t nc = 0;
   if (inside) {
     const float Tf = a.final_T[pix_id];
@@ -532,6 +535,10 @@ int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningW
     render_bwd_flat_kernel<2, 1><<<(ntiles * 4 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   } else if (v == 7) {
     render_bwd_flat_kernel<8, 1><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 8) {
+    render_bwd_flat_kernel<4, 1, true><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 9) {
+    render_bwd_flat_kernel<8, 1, true><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   } else {
     render_bwd_warp_kernel<8><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   }

@@ -76,7 +76,7 @@ def test_forward_matches_reference_cuda_bit_exact(fwd_variant):
         _lib.set_option("render_fwd_variant", 3)
 
 
-@pytest.mark.parametrize("bwd_variant", [0, 1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("bwd_variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_backward_matches_reference_cuda(bwd_variant):
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
@@ -97,7 +97,7 @@ def test_backward_matches_reference_cuda(bwd_variant):
                 assert err <= 1e-4 + 10 * noise, (name, a, err, noise)
                 assert np.abs(g - r).max() <= 1e-3 * np.abs(r).max() + 1e-12, (name, a)
     finally:
-        _lib.set_option("render_bwd_variant", 4)
+        _lib.set_option("render_bwd_variant", 8)
 
 
 def test_forward_backward_vs_cpu_oracle():
@@ -285,3 +285,12 @@ def test_speculative_second_half_equals_exact_path():
                 assert rel_l2(other["grads"][k].cpu().numpy(), exact["grads"][k].cpu().numpy()) <= 1e-5
     finally:
         RZ.SPECULATIVE = True
+
+
+def test_edit_loop_harness_runs_and_densifies():
+    """Config-5 loop shape (2 forwards + 1 backward per step, densification changing P) on a small cloud."""
+    from gaussianeditor_b200 import edit_loop
+    from gaussianeditor_b200.rasterizer import GaussianRasterizer
+    out = edit_loop.run_edit_loop(GaussianRasterizer, steps=8, P=20_000, densification_interval=3)
+    assert out["P_last"] != out["P_first"] and 0.0 < out["render_fraction"] < 1.0
+    assert np.isfinite(out["final_loss"])

@@ -1,0 +1,22 @@
+"""BASELINE config 5: 200 steps of the edit-n2n loop shape on the 500k-Gaussian stand-in scene, 512x512, ours vs the
+reference's CUDA build; prints one JSON line with the render-time fraction of each."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from gaussianeditor_b200 import edit_loop
+from gaussianeditor_b200.rasterizer import GaussianRasterizer
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+P = int(sys.argv[2]) if len(sys.argv) > 2 else None
+out = {"config": "c5: 500k Gaussians, SH deg 3, 512x512, 48 ring cameras, guidance stubbed by a fixed noisy target, L1 loss",
+       "ours": edit_loop.run_edit_loop(GaussianRasterizer, steps=steps, P=P)}
+try:
+    from oracle import ref_cuda, ref_torch
+    if ref_cuda.available():
+        out["reference"] = edit_loop.run_edit_loop(ref_torch.RefGaussianRasterizer, steps=steps, P=P)
+        out["step_speedup"] = out["reference"]["ms_per_step"] / out["ours"]["ms_per_step"]
+        out["render_speedup"] = out["reference"]["render_ms"] / out["ours"]["render_ms"]
+except Exception as ex:
+    out["reference_error"] = repr(ex)
+print(json.dumps(out))
+open(os.path.join(ROOT, "gpurun_out", "edit_loop.json"), "w").write(json.dumps(out, indent=1))

@@ -5,8 +5,8 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 from gaussianeditor_b200 import _lib
-fw = [int(x) for x in os.environ.get("FWD", "3,4").split(",")]
-bw = [int(x) for x in os.environ.get("BWD", "2,4,5").split(",")]
+fw = [int(x) for x in os.environ.get("FWD", "3").split(",")]
+bw = [int(x) for x in os.environ.get("BWD", "2,4,8,9").split(",")]
 wl = bench.Workload("c3", torch.device("cuda", 0))
 r = bench.OursRunner(wl)
 res = {}
