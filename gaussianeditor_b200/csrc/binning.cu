@@ -62,6 +62,7 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
 // once (32 consecutive slots span at most 32 visible ranks) and the lanes finish with a shuffle-only search.
 // Stores are fully coalesced.
 constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_CHUNKS = 8;  // consecutive 32-slot chunks per warp: the 32-ary search is paid once per 256 slots
 template <typename KeyT>
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(int P, uint32_t cap, const uint32_t* __restrict__ R_dev, KeyT pad_key,
@@ -71,49 +72,64 @@ emit_instances_kernel(int P, uint32_t cap, const uint32_t* __restrict__ R_dev, K
                       uint32_t* __restrict__ vals) {
   const unsigned F = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const uint32_t s0 = (blockIdx.x * EMIT_THREADS + threadIdx.x) - lane;  // first slot of this warp
+  const uint32_t warp_id = (blockIdx.x * EMIT_THREADS + threadIdx.x) >> 5;
+  const uint32_t s_begin = warp_id * (32u * EMIT_CHUNKS);
+  if (s_begin >= cap) return;
   // Speculative launches size the grid for a capacity `cap` >= R that the host guessed before R was known; R itself is
   // read from the scan result on the device and the slots [R, cap) get a key that sorts behind every tile.
   const uint32_t R = R_dev ? min(__ldg(R_dev), cap) : cap;
-  if (s0 >= R) {
-    if (s0 + lane < cap) { keys[s0 + lane] = pad_key; vals[s0 + lane] = 0u; }
-    return;
+  int r_base = 0;
+  if (s_begin < R) {
+    // smallest rank with offsets[rank] > s_begin; invariant: answer in [lo, lo+n), offsets[lo+n-1] > s_begin
+    int lo = 0, n = P;
+    while (n > 1) {  // warp-uniform
+      const int stride = (n + 31) >> 5;
+      const int pos = min(lo + (lane + 1) * stride - 1, lo + n - 1);
+      const unsigned gt = __ballot_sync(F, __ldg(offsets + pos) > s_begin);
+      const int j = __ffs(gt) - 1;
+      lo += j * stride;
+      n = min(stride, n - j * stride);
+    }
+    r_base = lo;
   }
-  // smallest rank r0 with offsets[r0] > s0; invariant: answer in [lo, lo+n), offsets[lo+n-1] > s0
-  int lo = 0, n = P;
-  while (n > 1) {  // warp-uniform
-    const int stride = (n + 31) >> 5;
-    const int pos = min(lo + (lane + 1) * stride - 1, lo + n - 1);
-    const unsigned gt = __ballot_sync(F, __ldg(offsets + pos) > s0);
-    const int j = __ffs(gt) - 1;
-    lo += j * stride;
-    n = min(stride, n - j * stride);
-  }
-  const int r0 = lo;
-  const uint32_t oj = __ldg(offsets + min(r0 + lane, P - 1));
-  const uint32_t s = min(s0 + lane, R - 1);
-  int c = 0;  // number of probed offsets <= s  (0..31)
+#pragma unroll 1
+  for (int ch = 0; ch < EMIT_CHUNKS; ch++) {
+    const uint32_t s0 = s_begin + 32u * ch;
+    if (s0 >= cap) break;
+    if (s0 >= R) {  // padding only
+      if (s0 + lane < cap) { keys[s0 + lane] = pad_key; vals[s0 + lane] = 0u; }
+      continue;
+    }
+    // r_base = smallest rank with offsets[r_base] > s0; 32 consecutive slots span at most 32 visible ranks
+    const uint32_t oj = __ldg(offsets + min(r_base + lane, P - 1));
+    const uint32_t s = min(s0 + lane, R - 1);
+    int c = 0;  // number of probed offsets <= s  (0..31)
 #pragma unroll
-  for (int step = 16; step > 0; step >>= 1) {
-    const uint32_t e = __shfl_sync(F, oj, c + step - 1);
-    if (e <= s) c += step;
-  }
-  const uint32_t end = __shfl_sync(F, oj, c);
-  const int rank = min(r0 + c, P - 1);
-  const uint32_t idx = order[rank];
-  const uint32_t start = end - tiles_touched[idx];
-  const float4 q0 = __ldg(reinterpret_cast<const float4*>(records + idx));
-  uint2 rmin, rmax;
-  tile_rect(q0.x, q0.y, radii[idx], gx, gy, rmin, rmax);
-  const uint32_t w = max(rmax.x - rmin.x, 1u);
-  const uint32_t k = s - start;
-  const uint32_t ry = k / w, rx = k - ry * w;
-  if (s0 + lane < R) {
-    keys[s] = (KeyT)((rmin.y + ry) * gx + (rmin.x + rx));
-    vals[s] = idx;
-  } else if (s0 + lane < cap) {
-    keys[s0 + lane] = pad_key;
-    vals[s0 + lane] = 0u;
+    for (int step = 16; step > 0; step >>= 1) {
+      const uint32_t e = __shfl_sync(F, oj, c + step - 1);
+      if (e <= s) c += step;
+    }
+    const uint32_t end = __shfl_sync(F, oj, c);
+    const int rank = min(r_base + c, P - 1);
+    const uint32_t idx = order[rank];
+    const uint32_t start = end - tiles_touched[idx];
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(records + idx));
+    uint2 rmin, rmax;
+    tile_rect(q0.x, q0.y, radii[idx], gx, gy, rmin, rmax);
+    const uint32_t w = max(rmax.x - rmin.x, 1u);
+    const uint32_t k = s - start;
+    const uint32_t ry = k / w, rx = k - ry * w;
+    if (s0 + lane < R) {
+      keys[s] = (KeyT)((rmin.y + ry) * gx + (rmin.x + rx));
+      vals[s] = idx;
+    } else if (s0 + lane < cap) {
+      keys[s0 + lane] = pad_key;
+      vals[s0 + lane] = 0u;
+    }
+    // next chunk starts at s0 + 32: the owner of slot s0+31 still owns it unless its range ends exactly there
+    const uint32_t end31 = __shfl_sync(F, end, 31);
+    const int rank31 = __shfl_sync(F, rank, 31);
+    r_base = rank31 + (end31 <= s0 + 32u ? 1 : 0);
   }
 }
 
@@ -210,7 +226,7 @@ int bin_typed(const gsr_cloud& c, int R, bool speculative, int gx, int gy, const
   int rc;
   {
     StageScope t(ST_EMIT, st);
-    emit_instances_kernel<KeyT><<<(R + EMIT_THREADS - 1) / EMIT_THREADS, EMIT_THREADS, 0, st>>>(
+    emit_instances_kernel<KeyT><<<(R + EMIT_THREADS * EMIT_CHUNKS - 1) / (EMIT_THREADS * EMIT_CHUNKS), EMIT_THREADS, 0, st>>>(
         c.P, (uint32_t)R, R_dev, pad_key, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, ku,
         b.vals_unsorted);
     g_launches++;

@@ -67,7 +67,7 @@ constexpr int ACC_STRIDE = 12;
 // ---- options -----------------------------------------------------------------------------------------
 struct Options {
   int render_fwd_variant = 3;  // 0 CTA/tile, 1/2/3 = 1/2/4 warps per tile
-  int render_bwd_variant = 8;  // 0 CTA/tile, 1/2/3 branchy 1/2/4 warps per tile, 4/5/6/7 branch-light variants
+  int render_bwd_variant = 4;  // 0 CTA/tile, 1/2/3 branchy 1/2/4 warps per tile, 4/5/6/7 branch-light variants
   int preprocess_variant = 1;
   int profile = 0;
   int tile_key_bits = 16;

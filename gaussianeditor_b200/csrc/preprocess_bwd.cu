@@ -255,102 +255,108 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
   }
 
   // ---- SH backward (backward.cu:20-139) ----
+  // Coefficient by coefficient, four at a time (12 floats = three 128-bit row accesses): read sh[k], add its share to the
+  // view-direction gradient, overwrite it IN PLACE with dL/dsh[k] = basis_k * dL/dRGB. Only one 12-float chunk is live
+  // at a time (the first version kept all 48 + 48 values in registers: 113 regs, 16 warps/SM).
   if (BULK) mbar_wait(&bar, 0);
   if (has_sh && live) {
-    float dsh[48];
-#pragma unroll
-    for (int i = 0; i < 48; i++) dsh[i] = 0.f;
+    const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
+    const float C2_0 = 1.0925484305920792f, C2_1 = -1.0925484305920792f, C2_2 = 0.31539156525252005f,
+                C2_3 = -1.0925484305920792f, C2_4 = 0.5462742152960396f;
+    const float C3_0 = -0.5900435899266435f, C3_1 = 2.890611442640554f, C3_2 = -0.4570457994644658f,
+                C3_3 = 0.3731763325901154f, C3_4 = -0.4570457994644658f, C3_5 = 1.445305721320277f,
+                C3_6 = -0.5900435899266435f;
+    float x = 0.f, y = 0.f, z = 0.f, sum2 = 1.f;
+    float3 dir_orig = make_float3(0.f, 0.f, 0.f);
+    float dRGB[3] = {0.f, 0.f, 0.f};
     if (vis) {
-      const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
-      const float C2_0 = 1.0925484305920792f, C2_1 = -1.0925484305920792f, C2_2 = 0.31539156525252005f,
-                  C2_3 = -1.0925484305920792f, C2_4 = 0.5462742152960396f;
-      const float C3_0 = -0.5900435899266435f, C3_1 = 2.890611442640554f, C3_2 = -0.4570457994644658f,
-                  C3_3 = 0.3731763325901154f, C3_4 = -0.4570457994644658f, C3_5 = 1.445305721320277f,
-                  C3_6 = -0.5900435899266435f;
-      float sh[48];
-      if (BULK) {
-        const int nvec = (nb * 3 + 3) >> 2;
+      dir_orig = make_float3(mean.x - a.campos[0], mean.y - a.campos[1], mean.z - a.campos[2]);
+      sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
+      const float len = sqrtf(sum2);
+      x = dir_orig.x / len; y = dir_orig.y / len; z = dir_orig.z / len;
+      const uint8_t cl = a.clamped[idx];
+      dRGB[0] = acc0.x * ((cl & 1) ? 0.f : 1.f);   // clamped channels pass no gradient (backward.cu:31-34)
+      dRGB[1] = acc0.y * ((cl & 2) ? 0.f : 1.f);
+      dRGB[2] = acc0.z * ((cl & 4) ? 0.f : 1.f);
+    }
+    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+    float ddir[3] = {0.f, 0.f, 0.f};
+    const float* gsrc = a.shs + (size_t)idx * a.M * 3;
+    float* gdst = a.dL_dsh + (size_t)idx * a.M * 3;
+    const int nw = a.M * 3;
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
-          float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < nvec) v4 = *reinterpret_cast<const float4*>(row + 4 * k);
-          sh[4 * k] = v4.x; sh[4 * k + 1] = v4.y; sh[4 * k + 2] = v4.z; sh[4 * k + 3] = v4.w;
+    for (int cchunk = 0; cchunk < 4; cchunk++) {
+      if (12 * cchunk >= nw) break;  // M = 4: one chunk, M = 16: four (M*12 % 16 == 0 on the BULK path)
+      float v[12];
+      const bool need = vis && 4 * cchunk < nb;  // this chunk holds active coefficients of a visible Gaussian
+      if (BULK) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (need) t4 = *reinterpret_cast<const float4*>(row + 12 * cchunk + 4 * q);
+          v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
         }
       } else {
-        const float* src = a.shs + (size_t)idx * a.M * 3;
 #pragma unroll
-        for (int i = 0; i < 48; i++) sh[i] = (i < nb * 3) ? src[i] : 0.f;
+        for (int i = 0; i < 12; i++) v[i] = (need && 12 * cchunk + i < nb * 3) ? gsrc[12 * cchunk + i] : 0.f;
       }
-      const float3 dir_orig = make_float3(mean.x - a.campos[0], mean.y - a.campos[1], mean.z - a.campos[2]);
-      const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-      const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-      const uint8_t cl = a.clamped[idx];
-      float dRGB[3] = {acc0.x * ((cl & 1) ? 0.f : 1.f), acc0.y * ((cl & 2) ? 0.f : 1.f), acc0.z * ((cl & 4) ? 0.f : 1.f)};
-      float bs[16];
+      float o12[12];
 #pragma unroll
-      for (int i = 0; i < 16; i++) bs[i] = 0.f;
-      float ddir[3] = {0.f, 0.f, 0.f};
-      bs[0] = C0;
-      if (a.D > 0) {
-        bs[1] = -C1 * y; bs[2] = C1 * z; bs[3] = -C1 * x;
-        float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-        if (a.D > 1) {
-          bs[4] = C2_0 * xy; bs[5] = C2_1 * yz; bs[6] = C2_2 * (2.f * zz - xx - yy); bs[7] = C2_3 * xz; bs[8] = C2_4 * (xx - yy);
-          if (a.D > 2) {
-            bs[9] = C3_0 * y * (3.f * xx - yy); bs[10] = C3_1 * xy * z; bs[11] = C3_2 * y * (4.f * zz - xx - yy);
-            bs[12] = C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); bs[13] = C3_4 * x * (4.f * zz - xx - yy);
-            bs[14] = C3_5 * z * (xx - yy); bs[15] = C3_6 * x * (xx - 3.f * yy);
-          }
+      for (int kk = 0; kk < 4; kk++) {
+        const int k = 4 * cchunk + kk;
+        // basis_k and its gradient w.r.t. the unit view direction (derivatives as backward.cu:58-122)
+        float bk = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+        switch (k) {
+          case 0: bk = C0; break;
+          case 1: bk = -C1 * y; by = -C1; break;
+          case 2: bk = C1 * z; bz = C1; break;
+          case 3: bk = -C1 * x; bx = -C1; break;
+          case 4: bk = C2_0 * xy; bx = C2_0 * y; by = C2_0 * x; break;
+          case 5: bk = C2_1 * yz; by = C2_1 * z; bz = C2_1 * y; break;
+          case 6: bk = C2_2 * (2.f * zz - xx - yy); bx = -2.f * C2_2 * x; by = -2.f * C2_2 * y; bz = 4.f * C2_2 * z; break;
+          case 7: bk = C2_3 * xz; bx = C2_3 * z; bz = C2_3 * x; break;
+          case 8: bk = C2_4 * (xx - yy); bx = 2.f * C2_4 * x; by = -2.f * C2_4 * y; break;
+          case 9: bk = C3_0 * y * (3.f * xx - yy); bx = 6.f * C3_0 * xy; by = 3.f * C3_0 * (xx - yy); break;
+          case 10: bk = C3_1 * xy * z; bx = C3_1 * yz; by = C3_1 * xz; bz = C3_1 * xy; break;
+          case 11: bk = C3_2 * y * (4.f * zz - xx - yy); bx = -2.f * C3_2 * xy; by = C3_2 * (-3.f * yy + 4.f * zz - xx); bz = 8.f * C3_2 * yz; break;
+          case 12: bk = C3_3 * z * (2.f * zz - 3.f * xx - 3.f * yy); bx = -6.f * C3_3 * xz; by = -6.f * C3_3 * yz; bz = 3.f * C3_3 * (2.f * zz - xx - yy); break;
+          case 13: bk = C3_4 * x * (4.f * zz - xx - yy); bx = C3_4 * (-3.f * xx + 4.f * zz - yy); by = -2.f * C3_4 * xy; bz = 8.f * C3_4 * xz; break;
+          case 14: bk = C3_5 * z * (xx - yy); bx = 2.f * C3_5 * xz; by = -2.f * C3_5 * yz; bz = C3_5 * (xx - yy); break;
+          default: bk = C3_6 * x * (xx - 3.f * yy); bx = 3.f * C3_6 * (xx - yy); by = -6.f * C3_6 * xy; break;
         }
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-          auto S = [&](int k) { return sh[3 * k + ch]; };
-          float dX = -C1 * S(3), dY = -C1 * S(1), dZ = C1 * S(2);
-          if (a.D > 1) {
-            dX += C2_0 * y * S(4) + C2_2 * 2.f * -x * S(6) + C2_3 * z * S(7) + C2_4 * 2.f * x * S(8);
-            dY += C2_0 * x * S(4) + C2_1 * z * S(5) + C2_2 * 2.f * -y * S(6) + C2_4 * 2.f * -y * S(8);
-            dZ += C2_1 * y * S(5) + C2_2 * 2.f * 2.f * z * S(6) + C2_3 * x * S(7);
-            if (a.D > 2) {
-              dX += (C3_0 * S(9) * 3.f * 2.f * xy + C3_1 * S(10) * yz + C3_2 * S(11) * -2.f * xy + C3_3 * S(12) * -3.f * 2.f * xz +
-                     C3_4 * S(13) * (-3.f * xx + 4.f * zz - yy) + C3_5 * S(14) * 2.f * xz + C3_6 * S(15) * 3.f * (xx - yy));
-              dY += (C3_0 * S(9) * 3.f * (xx - yy) + C3_1 * S(10) * xz + C3_2 * S(11) * (-3.f * yy + 4.f * zz - xx) +
-                     C3_3 * S(12) * -3.f * 2.f * yz + C3_4 * S(13) * -2.f * xy + C3_5 * S(14) * -2.f * yz + C3_6 * S(15) * -3.f * 2.f * xy);
-              dZ += (C3_1 * S(10) * xy + C3_2 * S(11) * 4.f * 2.f * yz + C3_3 * S(12) * 3.f * (2.f * zz - xx - yy) +
-                     C3_4 * S(13) * 4.f * 2.f * xz + C3_5 * S(14) * (xx - yy));
-            }
-          }
-          ddir[0] += dX * dRGB[ch];
-          ddir[1] += dY * dRGB[ch];
-          ddir[2] += dZ * dRGB[ch];
+        const bool active = need && k < nb;
+        // contribution of coefficient k to dL/ddir: (d basis_k / d dir) * (sh[k] . dL/dRGB)
+        const float dot = v[3 * kk] * dRGB[0] + v[3 * kk + 1] * dRGB[1] + v[3 * kk + 2] * dRGB[2];
+        if (active) {
+          ddir[0] = fmaf(bx, dot, ddir[0]);
+          ddir[1] = fmaf(by, dot, ddir[1]);
+          ddir[2] = fmaf(bz, dot, ddir[2]);
         }
+        o12[3 * kk] = active ? bk * dRGB[0] : 0.f;
+        o12[3 * kk + 1] = active ? bk * dRGB[1] : 0.f;
+        o12[3 * kk + 2] = active ? bk * dRGB[2] : 0.f;
       }
+      if (BULK) {
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        dsh[3 * k] = bs[k] * dRGB[0];
-        dsh[3 * k + 1] = bs[k] * dRGB[1];
-        dsh[3 * k + 2] = bs[k] * dRGB[2];
+        for (int q = 0; q < 3; q++)
+          *reinterpret_cast<float4*>(row + 12 * cchunk + 4 * q) = make_float4(o12[4 * q], o12[4 * q + 1], o12[4 * q + 2], o12[4 * q + 3]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 12; i++)
+          if (12 * cchunk + i < nw) gdst[12 * cchunk + i] = o12[i];
       }
+    }
+    if (vis) {
       // dnormvdv (auxiliary.h:107-117)
-      const float sum2 = dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z;
       const float invsum32 = 1.0f / sqrtf(sum2 * sum2 * sum2);
       dmean[0] += ((+sum2 - dir_orig.x * dir_orig.x) * ddir[0] - dir_orig.y * dir_orig.x * ddir[1] - dir_orig.z * dir_orig.x * ddir[2]) * invsum32;
       dmean[1] += (-dir_orig.x * dir_orig.y * ddir[0] + (sum2 - dir_orig.y * dir_orig.y) * ddir[1] - dir_orig.z * dir_orig.y * ddir[2]) * invsum32;
       dmean[2] += (-dir_orig.x * dir_orig.z * ddir[0] - dir_orig.y * dir_orig.z * ddir[1] + (sum2 - dir_orig.z * dir_orig.z) * ddir[2]) * invsum32;
     }
-    // ---- write the dL/dSH row (all M coefficients; zeros above the active degree / for culled Gaussians) ----
-    float* gdst = a.dL_dsh + (size_t)idx * a.M * 3;
-    const int nw = a.M * 3;
     if (BULK) {
-#pragma unroll
-      for (int k = 0; k < 12; k++)
-        if (4 * k < nw) *reinterpret_cast<float4*>(row + 4 * k) = make_float4(dsh[4 * k], dsh[4 * k + 1], dsh[4 * k + 2], dsh[4 * k + 3]);
       fence_proxy_async_smem();
       bulk_s2g(gdst, row, (uint32_t)(nw * 4));
       bulk_commit();
-    } else {
-#pragma unroll
-      for (int i = 0; i < 48; i++)
-        if (i < nw) gdst[i] = dsh[i];
     }
   }
 

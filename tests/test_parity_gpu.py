@@ -97,7 +97,7 @@ def test_backward_matches_reference_cuda(bwd_variant):
                 assert err <= 1e-4 + 10 * noise, (name, a, err, noise)
                 assert np.abs(g - r).max() <= 1e-3 * np.abs(r).max() + 1e-12, (name, a)
     finally:
-        _lib.set_option("render_bwd_variant", 8)
+        _lib.set_option("render_bwd_variant", 4)
 
 
 def test_forward_backward_vs_cpu_oracle():
