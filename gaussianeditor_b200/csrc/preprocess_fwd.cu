@@ -52,33 +52,53 @@ struct PreArgs {
   int32_t* radii;
 };
 
-// SH basis-weighted sum, one colour channel; `sh(k)` yields coefficient k of this channel.
-// Order of operations as forward.cu:30-61.
-template <typename ShFn>
-__device__ __forceinline__ float sh_channel(int deg, float x, float y, float z, ShFn sh) {
+// SH basis weights of forward.cu:30-61 for the unit view direction (x,y,z), pinned to the operation sequence nvcc emits
+// for the reference (decoded from its SASS): every weight is a product of plain multiplications in this association,
+// the polynomial factors use the FMA forms noted, and each colour channel is one FMA chain res = fma(w_k, sh_k, res)
+// in ascending k starting from C0*sh_0. Signs of k = 1, 3 are folded into the weight (exact).
+__device__ __forceinline__ void sh_weights(int deg, float x, float y, float z, float* w) {
   const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
   const float C2_0 = 1.0925484305920792f, C2_1 = -1.0925484305920792f, C2_2 = 0.31539156525252005f,
               C2_3 = -1.0925484305920792f, C2_4 = 0.5462742152960396f;
   const float C3_0 = -0.5900435899266435f, C3_1 = 2.890611442640554f, C3_2 = -0.4570457994644658f,
               C3_3 = 0.3731763325901154f, C3_4 = -0.4570457994644658f, C3_5 = 1.445305721320277f,
               C3_6 = -0.5900435899266435f;
-  float result = C0 * sh(0);
+  w[0] = C0;
   if (deg > 0) {
-    result = result - C1 * y * sh(1) + C1 * z * sh(2) - C1 * x * sh(3);
+    w[1] = -__fmul_rn(y, C1);
+    w[2] = __fmul_rn(z, C1);
+    w[3] = -__fmul_rn(x, C1);
     if (deg > 1) {
-      float xx = x * x, yy = y * y, zz = z * z;
-      float xy = x * y, yz = y * z, xz = x * z;
-      result = result + C2_0 * xy * sh(4) + C2_1 * yz * sh(5) + C2_2 * (2.0f * zz - xx - yy) * sh(6) +
-               C2_3 * xz * sh(7) + C2_4 * (xx - yy) * sh(8);
+      const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+      const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
+      const float zz2 = __fadd_rn(zz, zz);
+      const float xx_yy = __fadd_rn(xx, -yy);
+      w[4] = __fmul_rn(xy, C2_0);
+      w[5] = __fmul_rn(yz, C2_1);
+      w[6] = __fmul_rn(__fadd_rn(__fadd_rn(zz2, -xx), -yy), C2_2);   // (2zz - xx) - yy
+      w[7] = __fmul_rn(xz, C2_3);
+      w[8] = __fmul_rn(xx_yy, C2_4);
       if (deg > 2) {
-        result = result + C3_0 * y * (3.0f * xx - yy) * sh(9) + C3_1 * xy * z * sh(10) +
-                 C3_2 * y * (4.0f * zz - xx - yy) * sh(11) + C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh(12) +
-                 C3_4 * x * (4.0f * zz - xx - yy) * sh(13) + C3_5 * z * (xx - yy) * sh(14) +
-                 C3_6 * x * (xx - 3.0f * yy) * sh(15);
+        const float p4 = __fadd_rn(__fmaf_rn(zz, 4.0f, -xx), -yy);   // (4zz - xx) - yy
+        w[9] = __fmul_rn(__fmul_rn(y, C3_0), __fmaf_rn(xx, 3.0f, -yy));
+        w[10] = __fmul_rn(__fmul_rn(xy, C3_1), z);
+        w[11] = __fmul_rn(__fmul_rn(y, C3_2), p4);
+        w[12] = __fmul_rn(__fmul_rn(z, C3_3), __fmaf_rn(yy, -3.0f, __fmaf_rn(xx, -3.0f, zz2)));
+        w[13] = __fmul_rn(__fmul_rn(x, C3_4), p4);
+        w[14] = __fmul_rn(xx_yy, __fmul_rn(z, C3_5));
+        w[15] = __fmul_rn(__fmul_rn(x, C3_6), __fmaf_rn(yy, -3.0f, xx));
       }
     }
   }
-  return result + 0.5f;
+}
+template <typename ShFn>
+__device__ __forceinline__ float sh_channel(int deg, const float* w, ShFn sh) {
+  float res = __fmul_rn(sh(0), w[0]);
+  const int nb = (deg + 1) * (deg + 1);
+#pragma unroll
+  for (int k = 1; k < 16; k++)
+    if (k < nb) res = __fmaf_rn(w[k], sh(k), res);
+  return __fadd_rn(res, 0.5f);
 }
 
 template <bool BULK_SH>
@@ -255,11 +275,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     if (!want_sh) {
       rgb = make_float3(a.colors_precomp[3 * idx], a.colors_precomp[3 * idx + 1], a.colors_precomp[3 * idx + 2]);
     } else {
-      float3 dir = make_float3(p_orig.x - a.campos[0], p_orig.y - a.campos[1], p_orig.z - a.campos[2]);
-      float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-      dir.x = dir.x / len;
-      dir.y = dir.y / len;
-      dir.z = dir.z / len;
+      float3 dir = make_float3(__fadd_rn(p_orig.x, -a.campos[0]), __fadd_rn(p_orig.y, -a.campos[1]),
+                               __fadd_rn(p_orig.z, -a.campos[2]));
+      const float len = __fsqrt_rn(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.x, dir.x, __fmul_rn(dir.y, dir.y))));
+      dir.x = __fdiv_rn(dir.x, len);
+      dir.y = __fdiv_rn(dir.y, len);
+      dir.z = __fdiv_rn(dir.z, len);
+      float w[16];
+      sh_weights(a.D, dir.x, dir.y, dir.z, w);
       float res[3];
       if (BULK_SH) {
         const float* row = &sh_rows[threadIdx.x * SH_ROW_WORDS];
@@ -276,11 +299,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
           }
         }
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) res[ch] = sh_channel(a.D, dir.x, dir.y, dir.z, [&](int k) { return v[3 * k + ch]; });
+        for (int ch = 0; ch < 3; ch++) res[ch] = sh_channel(a.D, w, [&](int k) { return v[3 * k + ch]; });
       } else {
         const float* sh = a.shs + (size_t)idx * a.M * 3;
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) res[ch] = sh_channel(a.D, dir.x, dir.y, dir.z, [&](int k) { return sh[3 * k + ch]; });
+        for (int ch = 0; ch < 3; ch++) res[ch] = sh_channel(a.D, w, [&](int k) { return sh[3 * k + ch]; });
       }
       clamp_bits = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
       rgb = make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));

@@ -162,4 +162,4 @@ def run_edit_loop(rasterizer_cls, steps=200, P=None, device="cuda", densificatio
     finally:
         GR.GaussianRasterizer = old
     return dict(steps=steps, total_ms=total_ms, render_ms=render_ms, render_fraction=render_ms / total_ms,
-                ms_per_step=total_ms / steps, P_first=counts[0], P_last=counts[-1], final_loss=float(loss))
+                ms_per_step=total_ms / steps, P_first=counts[0], P_last=counts[-1], final_loss=float(loss.detach()))

@@ -294,3 +294,88 @@ def test_edit_loop_harness_runs_and_densifies():
     out = edit_loop.run_edit_loop(GaussianRasterizer, steps=8, P=20_000, densification_interval=3)
     assert out["P_last"] != out["P_first"] and 0.0 < out["render_fraction"] < 1.0
     assert np.isfinite(out["final_loss"])
+
+
+def _grad_close(ours, ref, pairs, name, tol=1e-4):
+    for a, b in pairs:
+        g = ours["grads"][a]
+        if g is None:
+            continue
+        r = ref["grads"][b].cpu().numpy()
+        err = rel_l2(g.cpu().numpy().reshape(r.shape), r)
+        assert err <= tol, (name, a, err)
+
+
+@pytest.mark.parametrize("deg,M", [(0, 16), (1, 16), (2, 16), (3, 16), (1, 4), (2, 9), (0, 1)])
+def test_sh_degrees_and_coefficient_counts(deg, M):
+    """Active degree below the allocated one (GaussianEditor ramps sh_degree up), M = 4 / 16 take the TMA row path,
+    M = 1 / 9 the plain-load path; coefficients above the active degree must get exactly zero gradient."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    cloud, _ = synth.make_config("c3", P=30_000)
+    cloud.shs = np.ascontiguousarray(cloud.shs[:, :M, :])
+    cloud.sh_degree = deg
+    cam = synth.ring_cameras(8, 4.5, 15.0, 208, 160, 61.0)[3]
+    dL = np.random.default_rng(deg * 7 + M).uniform(size=(3, 160, 208)).astype(np.float32)
+    ours = run_ours(cloud, cam, (0.1, 0.1, 0.1), dL=dL)
+    ref = _ref_run(cloud, cam, (0.1, 0.1, 0.1), dL=dL)
+    assert torch.equal(ours["radii"], ref["radii"]) and torch.equal(ours["color"], ref["color"])
+    vis = ours["radii"] > 0
+    assert torch.equal(ours["views"]["records"][vis][:, 8:11], ref["state"]["rgb"][vis])
+    cl = ours["views"]["clamped"][vis]
+    rc = ref["state"]["clamped"][vis]
+    assert torch.equal(cl, (rc[:, 0] + 2 * rc[:, 1] + 4 * rc[:, 2]).to(torch.uint8))
+    _grad_close(ours, ref, [("dsh", "dL_dsh"), ("dmean3D", "dL_dmeans3D"), ("dopacity", "dL_dopacity")], (deg, M))
+    nb = (deg + 1) ** 2
+    assert float(ours["grads"]["dsh"][:, nb:, :].abs().sum()) == 0.0
+
+
+def test_precomputed_covariance_path():
+    """cov3D_precomp instead of scale/rotation (unused by GaussianEditor but part of the API): forward bit-exact,
+    dL/dcov3D to tolerance, scale/rotation gradients absent."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    from gaussianeditor_b200.rasterizer import GaussianRasterizer
+    dev = "cuda"
+    cloud, _ = synth.make_config("c3", P=20_000)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 192, 144, 61.0)[5]
+    f = cpu_oracle.forward_from(cloud, cam, render=False)          # cov3D from the oracle as the precomputed input
+    cov = torch.from_numpy(f.cov3D.astype(np.float32)).to(dev).requires_grad_(True)
+    f.close()
+    ct = cloud_tensors(cloud, dev, requires_grad=True)
+    rs = settings_from(cam, (0, 0, 0), 3, dev)
+    m2 = torch.zeros_like(ct["means3D"], requires_grad=True)
+    color, radii, depth = GaussianRasterizer(rs)(means3D=ct["means3D"], means2D=m2, opacities=ct["opacities"],
+                                                 shs=ct["shs"], cov3D_precomp=cov)
+    dL = torch.rand(3, 144, 192, device=dev)
+    (color * dL).sum().backward()
+    R = ref_cuda.ReferenceRasterizer()
+    common = dict(means3D=ct["means3D"].detach(), shs=ct["shs"].detach(), colors_precomp=None, scales=None, rotations=None,
+                  cov3D_precomp=cov.detach(), bg=rs.bg, viewmatrix=rs.viewmatrix, projmatrix=rs.projmatrix,
+                  campos=rs.campos, tanfovx=rs.tanfovx, tanfovy=rs.tanfovy, sh_degree=3)
+    rc, rr, rd, n = R.forward(opacities=ct["opacities"].detach(), image_height=144, image_width=192, **common)
+    g = R.backward(dL_dcolor=dL, radii=rr, R=n, **common)
+    assert torch.equal(radii, rr) and torch.equal(color.detach(), rc)
+    assert rel_l2(cov.grad.cpu().numpy(), g["dL_dcov3D"].cpu().numpy()) <= 1e-4
+    assert rel_l2(ct["means3D"].grad.cpu().numpy(), g["dL_dmeans3D"].cpu().numpy()) <= 1e-4
+
+
+def test_hd_frame_partial_tile_row_and_debug_flag():
+    """1920x1080: 1080 is not a multiple of 16 (68 tile rows, last partial); debug=True synchronises after each launch."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    from gaussianeditor_b200.rasterizer import GaussianRasterizer, _RasterizeGaussians, forward_state_views
+    dev = "cuda"
+    cloud, _ = synth.make_config("c3", P=150_000)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 1920, 1080, 61.0)[1]
+    ct = cloud_tensors(cloud, dev)
+    rs = settings_from(cam, (0.3, 0.6, 0.9), 3, dev, debug=True)
+    color, radii, depth = GaussianRasterizer(rs)(means3D=ct["means3D"], means2D=torch.zeros_like(ct["means3D"]),
+                                                 opacities=ct["opacities"], shs=ct["shs"], scales=ct["scales"],
+                                                 rotations=ct["rotations"])
+    ref = _ref_run(cloud, cam, (0.3, 0.6, 0.9))
+    v = forward_state_views(_RasterizeGaussians.last_state)
+    assert v["ranges"].shape[0] == 120 * 68
+    assert torch.equal(radii, ref["radii"]) and torch.equal(v["ranges"], ref["state"]["ranges"])
+    assert torch.equal(color, ref["color"]) and torch.equal(depth, ref["depth"])
+    assert torch.equal(v["n_contrib"], ref["state"]["n_contrib"])
