@@ -21,6 +21,8 @@ SYMBOLS = [
     "gsr_mark_visible", "gsr_apply_weights", "gsr_view_geometry", "gsr_view_binning", "gsr_view_image",
     "gsr_set_option", "gsr_get_option", "gsr_launch_count", "gsr_profile_read", "gsr_host_create", "gsr_host_destroy",
     "gsr_host_upload_cloud", "gsr_host_step",
+    "gsr_view_exchange", "gsr_shard_preprocess", "gsr_shard_order", "gsr_shard_render", "gsr_shard_backward_render",
+    "gsr_shard_backward_preprocess",
 ]
 
 
@@ -60,6 +62,14 @@ class BinningView(C.Structure):
 
 class ImageView(C.Structure):
     _fields_ = [("final_T", C.c_void_p), ("n_contrib", C.c_void_p), ("ranges", C.c_void_p)]
+
+
+class TileOwner(C.Structure):
+    _fields_ = [("row_stride", C.c_int32), ("row_phase", C.c_int32)]
+
+
+class ExchangeView(C.Structure):
+    _fields_ = [("records", C.c_void_p)]
 
 
 _lib = None
@@ -118,7 +128,19 @@ def load():
     lib.gsr_host_upload_cloud.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     lib.gsr_host_step.restype = i64
     lib.gsr_host_step.argtypes = [vp, C.POINTER(Settings), vp, vp, vp, vp]
-    if lib.gsr_abi_version() != 1:
+    S, Cl, TO = C.POINTER(Settings), C.POINTER(Cloud), C.POINTER(TileOwner)
+    lib.gsr_view_exchange.restype = C.c_int; lib.gsr_view_exchange.argtypes = [vp, i32, C.POINTER(ExchangeView)]
+    lib.gsr_shard_preprocess.restype = C.c_int
+    lib.gsr_shard_preprocess.argtypes = [S, Cl, i32, i32, i32, vp, sz, vp, vp]
+    lib.gsr_shard_order.restype = C.c_int
+    lib.gsr_shard_order.argtypes = [S, TO, i32, vp, sz, vp, vp, vp]
+    lib.gsr_shard_render.restype = C.c_int
+    lib.gsr_shard_render.argtypes = [S, TO, i32, i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp]
+    lib.gsr_shard_backward_render.restype = C.c_int
+    lib.gsr_shard_backward_render.argtypes = [S, TO, i32, i32, vp, sz, vp, sz, vp, sz, vp, vp, sz, vp]
+    lib.gsr_shard_backward_preprocess.restype = C.c_int
+    lib.gsr_shard_backward_preprocess.argtypes = [S, Cl, i32, i32, vp, sz, vp, vp, C.POINTER(Grads), vp]
+    if lib.gsr_abi_version() != 2:
         raise RuntimeError("libgsr_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -233,6 +233,152 @@ int gsr_apply_weights(const gsr_settings* s, const gsr_cloud* c, int32_t R, void
   return launch_apply_weights(*s, g, b, im, image_weights, CH, weights, cnt, st);
 }
 
+// ---- Gaussian-sharded multi-GPU path ---------------------------------------------------------------------
+static int check_owner(const gsr_tile_owner* o, TileOwner& own) {
+  if (!o || o->row_stride < 1 || o->row_phase < 0 || o->row_phase >= o->row_stride) {
+    set_error("tile owner: need row_stride >= 1 and 0 <= row_phase < row_stride");
+    return GSR_ERR_INVALID;
+  }
+  own.stride = o->row_stride; own.phase = o->row_phase;
+  return GSR_OK;
+}
+static int check_settings(const gsr_settings* s) {
+  if (!s) { set_error("null settings"); return GSR_ERR_INVALID; }
+  if (s->image_width < 0 || s->image_height < 0) { set_error("negative size"); return GSR_ERR_INVALID; }
+  if (!s->bg || !s->viewmatrix || !s->projmatrix || !s->campos) { set_error("camera pointers must not be null"); return GSR_ERR_INVALID; }
+  return GSR_OK;
+}
+// the slice [base, base+n) of the per-Gaussian arrays of a P_total-sized geometry workspace
+static GeometryWS slice_geometry(const GeometryWS& g, int base) {
+  GeometryWS l = g;
+  l.records += base; l.tiles_touched += base; l.clamped += base; l.depth_keys += base; l.ident += base;
+  return l;
+}
+
+int gsr_view_exchange(void* geometry, int32_t P_total, gsr_exchange_view* out) {
+  GeometryWS g;
+  if (!out || P_total < 0 || !carve_geometry(geometry, P_total, g)) return GSR_ERR_INVALID;
+  out->records = g.records;
+  return GSR_OK;
+}
+
+int gsr_shard_preprocess(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
+                         int32_t slice_len, void* geometry, size_t geometry_bytes, int32_t* radii_total, void* stream) {
+  int rc = validate(s, shard);
+  if (rc) return rc;
+  if (P_total <= 0 || index_base < 0 || slice_len < shard->P || (int64_t)index_base + slice_len > P_total) {
+    set_error("shard [%d, %d+%d) (P=%d) does not fit P_total=%d", index_base, index_base, slice_len, shard->P, P_total);
+    return GSR_ERR_INVALID;
+  }
+  if (!radii_total || !geometry) { set_error("radii / geometry workspace is null"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  GeometryWS g;
+  if (!carve_geometry(geometry, P_total, g)) return GSR_ERR_CUDA;
+  if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
+  StageScope t(ST_PRE_FWD, st);
+  if (shard->P > 0) {
+    rc = launch_preprocess_fwd(*s, *shard, slice_geometry(g, index_base), radii_total + index_base, st);
+    if (rc) return rc;
+  }
+  const int pad = slice_len - shard->P;  // slots of the slice behind the shard: culled (radius 0 in the record)
+  if (pad > 0) {
+    cudaError_t e = cudaMemsetAsync(g.records + index_base + shard->P, 0, (size_t)pad * sizeof(SplatRecord), st);
+    if (e != cudaSuccess) return check_cuda(e, "slice padding");
+  }
+  return GSR_OK;
+}
+
+int gsr_shard_order(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total, void* geometry,
+                    size_t geometry_bytes, int32_t* radii_total, int32_t* num_rendered_host, void* stream) {
+  int rc = check_settings(s);
+  if (rc) return rc;
+  TileOwner own;
+  rc = check_owner(owner, own);
+  if (rc) return rc;
+  if (P_total <= 0 || !geometry || !radii_total || !num_rendered_host) { set_error("shard_order: bad arguments"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  GeometryWS g;
+  if (!carve_geometry(geometry, P_total, g)) return GSR_ERR_CUDA;
+  if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
+  StageScope t(ST_DEPTH_SCAN, st);
+  rc = launch_retouch(*s, P_total, g, radii_total, own, st);
+  if (rc) return rc;
+  gsr_cloud c{};
+  c.P = P_total;
+  return run_depth_order_and_scan(c, g, num_rendered_host, st, s->debug != 0);
+}
+
+int gsr_shard_render(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total, int32_t R, void* geometry,
+                     size_t geometry_bytes, void* binning, size_t binning_bytes, void* image, size_t image_bytes,
+                     const int32_t* radii_total, float* out_color, float* out_depth, void* stream) {
+  int rc = check_settings(s);
+  if (rc) return rc;
+  TileOwner own;
+  rc = check_owner(owner, own);
+  if (rc) return rc;
+  if (P_total <= 0 || R < 0 || !out_color || !out_depth || !radii_total) { set_error("shard_render: bad arguments"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  gsr_cloud c{};
+  c.P = P_total;
+  GeometryWS g; BinningWS b; ImageWS im;
+  rc = carve_all(s, &c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, g, b, im);
+  if (rc) return rc;
+  rc = run_binning(*s, c, R, false, g, b, im, radii_total, st, own);
+  if (rc) return rc;
+  StageScope t(ST_RENDER_FWD, st);
+  return launch_render_fwd(*s, g, b, im, out_color, out_depth, st, own);
+}
+
+int gsr_shard_backward_render(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total, int32_t R,
+                              const void* geometry, size_t geometry_bytes, const void* binning, size_t binning_bytes,
+                              const void* image, size_t image_bytes, const float* dL_dout_color, void* acc_total,
+                              size_t acc_bytes, void* stream) {
+  int rc = check_settings(s);
+  if (rc) return rc;
+  TileOwner own;
+  rc = check_owner(owner, own);
+  if (rc) return rc;
+  if (P_total <= 0 || R < 0 || !dL_dout_color) { set_error("shard_backward_render: bad arguments"); return GSR_ERR_INVALID; }
+  const size_t need = (size_t)P_total * ACC_STRIDE * sizeof(float);
+  if (!acc_total || acc_bytes < need) { set_error("accumulators too small: %zu < %zu", acc_bytes, need); return GSR_ERR_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  gsr_cloud c{};
+  c.P = P_total;
+  GeometryWS g; BinningWS b; ImageWS im;
+  rc = carve_all(s, &c, R, const_cast<void*>(geometry), geometry_bytes, const_cast<void*>(binning), binning_bytes,
+                 const_cast<void*>(image), image_bytes, g, b, im);
+  if (rc) return rc;
+  StageScope t(ST_RENDER_BWD, st);
+  cudaError_t e = cudaMemsetAsync(acc_total, 0, need, st);
+  if (e != cudaSuccess) return check_cuda(e, "accumulator memset");
+  if (R == 0) return GSR_OK;
+  return launch_render_bwd(*s, g, b, im, dL_dout_color, (float*)acc_total, st, own);
+}
+
+int gsr_shard_backward_preprocess(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
+                                  const void* geometry, size_t geometry_bytes, const int32_t* radii_total,
+                                  const void* acc_slice, const gsr_grads* gr, void* stream) {
+  int rc = validate(s, shard);
+  if (rc) return rc;
+  if (P_total <= 0 || index_base < 0 || (int64_t)index_base + shard->P > P_total) { set_error("shard does not fit P_total"); return GSR_ERR_INVALID; }
+  if (shard->P == 0) return GSR_OK;
+  if (!gr || !acc_slice || !radii_total) { set_error("grads / accumulators / radii is null"); return GSR_ERR_INVALID; }
+  if (!gr->dL_dmeans3D || !gr->dL_dmeans2D || !gr->dL_dcolors || !gr->dL_dopacity || !gr->dL_dcov3D ||
+      !gr->dL_dscales || !gr->dL_drotations || (shard->shs && !gr->dL_dsh)) {
+    set_error("a gradient output pointer is null");
+    return GSR_ERR_INVALID;
+  }
+  if (reinterpret_cast<uintptr_t>(gr->dL_drotations) & 15) { set_error("dL_drotations must be 16-byte aligned"); return GSR_ERR_INVALID; }
+  if (reinterpret_cast<uintptr_t>(acc_slice) & 15) { set_error("acc_slice must be 16-byte aligned"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  GeometryWS g;
+  if (!carve_geometry(const_cast<void*>(geometry), P_total, g)) return GSR_ERR_CUDA;
+  if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
+  StageScope t(ST_PRE_BWD, st);
+  return launch_preprocess_bwd(*s, *shard, slice_geometry(g, index_base), radii_total + index_base,
+                               (const float*)acc_slice, *gr, st);
+}
+
 int gsr_view_geometry(const void* geometry, int32_t P, gsr_geometry_view* out) {
   GeometryWS g;
   if (!out || !carve_geometry(const_cast<void*>(geometry), P, g)) return GSR_ERR_INVALID;

@@ -54,6 +54,44 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
   rmax.y = (unsigned)min(gy, max((int)0, (int)((py + radius + TILE - 1) / TILE)));
 }
 
+// Rows of the rectangle [rmin.y, rmax.y) this rank owns (ty % stride == phase): first owned row and their number.
+__device__ __forceinline__ void owned_rows(uint32_t ymin, uint32_t ymax, int stride, int phase, uint32_t& y0, uint32_t& ny) {
+  if (stride == 1) { y0 = ymin; ny = ymax - ymin; return; }
+  int d = (phase - (int)ymin) % stride;
+  if (d < 0) d += stride;
+  y0 = ymin + (uint32_t)d;
+  ny = y0 < ymax ? (ymax - y0 + (uint32_t)stride - 1u) / (uint32_t)stride : 0u;
+}
+
+// Sharded path, after the all-gather of the splat records: rebuild the per-Gaussian arrays of all P Gaussians from
+// the records (radius = q2.w, depth key = bits of q1.z), count the OWNED tiles and write the identity permutation the
+// depth sort carries. A Gaussian that touches none of this rank's tile rows gets the "culled" depth key, so that --
+// as on a single GPU -- every Gaussian with a zero count sorts behind all the others (emit_instances_kernel relies on
+// it: 32 consecutive instance slots then span at most 32 depth ranks). Its position in the order is irrelevant: it
+// emits nothing.
+__global__ void retouch_kernel(int P, const SplatRecord* __restrict__ records, int gx, int gy, int stride, int phase,
+                               int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
+                               uint32_t* __restrict__ ident, uint32_t* __restrict__ depth_keys) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= P) return;
+  const float4* r = reinterpret_cast<const float4*>(records + idx);
+  const int radius = __float_as_int(__ldg(r + 2).w);
+  uint32_t n = 0, key = 0xFFFFFFFFu;
+  if (radius > 0) {
+    const float4 q0 = __ldg(r);
+    uint2 rmin, rmax;
+    tile_rect(q0.x, q0.y, radius, gx, gy, rmin, rmax);
+    uint32_t y0, ny;
+    owned_rows(rmin.y, rmax.y, stride, phase, y0, ny);
+    n = ny * (rmax.x - rmin.x);
+    if (n != 0) key = __float_as_uint(__ldg(r + 1).z);
+  }
+  radii[idx] = radius;
+  tiles_touched[idx] = n;
+  ident[idx] = (uint32_t)idx;
+  depth_keys[idx] = key;
+}
+
 // One thread per OUTPUT slot (instance): perfectly balanced no matter how the tile counts are distributed --
 // in depth order the few huge near-camera splats (thousands of tiles each) are adjacent ranks, so any
 // rank-to-thread or rank-to-warp assignment serialises them. Finding the owner rank of a slot is a search over the
@@ -68,8 +106,8 @@ __global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(int P, uint32_t cap, const uint32_t* __restrict__ R_dev, KeyT pad_key,
                       const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                       const uint32_t* __restrict__ tiles_touched, const SplatRecord* __restrict__ records,
-                      const int32_t* __restrict__ radii, int gx, int gy, KeyT* __restrict__ keys,
-                      uint32_t* __restrict__ vals) {
+                      const int32_t* __restrict__ radii, int gx, int gy, int own_stride, int own_phase,
+                      KeyT* __restrict__ keys, uint32_t* __restrict__ vals) {
   const unsigned F = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const uint32_t warp_id = (blockIdx.x * EMIT_THREADS + threadIdx.x) >> 5;
@@ -119,8 +157,10 @@ emit_instances_kernel(int P, uint32_t cap, const uint32_t* __restrict__ R_dev, K
     const uint32_t w = max(rmax.x - rmin.x, 1u);
     const uint32_t k = s - start;
     const uint32_t ry = k / w, rx = k - ry * w;
+    uint32_t y0, ny;
+    owned_rows(rmin.y, rmax.y, own_stride, own_phase, y0, ny);
     if (s0 + lane < R) {
-      keys[s] = (KeyT)((rmin.y + ry) * gx + (rmin.x + rx));
+      keys[s] = (KeyT)((y0 + ry * (uint32_t)own_stride) * gx + (rmin.x + rx));
       vals[s] = idx;
     } else if (s0 + lane < cap) {
       keys[s0 + lane] = pad_key;
@@ -217,7 +257,7 @@ size_t tile_sort_temp_bytes(int64_t R) {
 
 template <typename KeyT>
 int bin_typed(const gsr_cloud& c, int R, bool speculative, int gx, int gy, const GeometryWS& g, const BinningWS& b,
-              const ImageWS& im, const int32_t* radii, cudaStream_t st, bool debug) {
+              const ImageWS& im, const int32_t* radii, cudaStream_t st, bool debug, const TileOwner& own) {
   const uint32_t* R_dev = speculative ? g.offsets + (c.P - 1) : nullptr;
   const int bit = (int)higher_msb((uint32_t)(gx * gy));
   const KeyT pad_key = (KeyT)((1u << bit) - 1u);  // > every tile id (ids <= Ntile-1 <= 2^bit - 2), inside the sorted bits
@@ -227,8 +267,8 @@ int bin_typed(const gsr_cloud& c, int R, bool speculative, int gx, int gy, const
   {
     StageScope t(ST_EMIT, st);
     emit_instances_kernel<KeyT><<<(R + EMIT_THREADS * EMIT_CHUNKS - 1) / (EMIT_THREADS * EMIT_CHUNKS), EMIT_THREADS, 0, st>>>(
-        c.P, (uint32_t)R, R_dev, pad_key, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, ku,
-        b.vals_unsorted);
+        c.P, (uint32_t)R, R_dev, pad_key, g.depth_order, g.offsets, g.tiles_touched, g.records, radii, gx, gy, own.stride,
+        own.phase, ku, b.vals_unsorted);
     g_launches++;
     rc = check_launch("emit_instances", debug, st);
     if (rc) return rc;
@@ -338,7 +378,7 @@ int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* n
 }
 
 int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculative, const GeometryWS& g,
-                const BinningWS& b, const ImageWS& im, const int32_t* radii, cudaStream_t st) {
+                const BinningWS& b, const ImageWS& im, const int32_t* radii, cudaStream_t st, const TileOwner& own) {
   const int W = s.image_width, H = s.image_height;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const bool debug = s.debug != 0;
@@ -347,8 +387,17 @@ int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculati
   if (R <= 0) return GSR_OK;
   // tile ids fit 16 bits for every image up to 4096x4096 (65536 tiles): half the key traffic of the sort
   if ((int64_t)gx * gy <= 65536 && g_opt.tile_key_bits == 16)
-    return bin_typed<uint16_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug);
-  return bin_typed<uint32_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug);
+    return bin_typed<uint16_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug, own);
+  return bin_typed<uint32_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug, own);
+}
+
+int launch_retouch(const gsr_settings& s, int P, const GeometryWS& g, int32_t* radii, const TileOwner& own,
+                   cudaStream_t st) {
+  const int gx = (s.image_width + TILE - 1) / TILE, gy = (s.image_height + TILE - 1) / TILE;
+  retouch_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, g.records, gx, gy, own.stride, own.phase, radii, g.tiles_touched,
+                                                  g.ident, g.depth_keys);
+  g_launches++;
+  return check_launch("retouch", s.debug != 0, st);
 }
 
 }  // namespace gsr

@@ -17,7 +17,7 @@ constexpr int TILE_PIX = TILE * TILE;
 // into 48 contiguous, 16-byte-aligned bytes so that one tile-list gather is three 128-bit loads
 // (the reference gathers from five separate arrays: means2D, conic_opacity, rgb, depths, point ids).
 //   q0 = { x, y, conic.a, conic.b }      q1 = { conic.c, opacity, view-depth, <unused> }
-//   q2 = { r, g, b, <unused> }
+//   q2 = { r, g, b, radius (int bits; 0 = culled, the only field a culled record defines) }
 struct __align__(16) SplatRecord {
   float4 q0, q1, q2;
 };
@@ -53,6 +53,13 @@ struct ImageWS {
   uint2* ranges;        // [Ntile]
   uint32_t* tile_last;  // [Ntile] max n_contrib over the tile's pixels: where the backward walk starts
   size_t total;
+};
+
+// Tile ownership of the Gaussian-sharded multi-GPU path (gsr_b200.h: gsr_tile_owner): this rank bins and renders the
+// tile rows ty with ty % stride == phase. {1, 0} = every tile (single-GPU path).
+struct TileOwner {
+  int stride = 1, phase = 0;
+  int owned_rows(int gy) const { return phase < gy ? (gy - phase + stride - 1) / stride : 0; }
 };
 
 // Carve a workspace out of `base` (may be null for a pure size query).
@@ -93,12 +100,16 @@ int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const Geome
                           cudaStream_t st);
 int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
                              bool debug);
+// Sharded path: recompute tiles_touched (owned tile rows only) and the sort identity for all P gathered Gaussians.
+int launch_retouch(const gsr_settings& s, int P, const GeometryWS& g, int32_t* radii, const TileOwner& own,
+                   cudaStream_t st);
 int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculative, const GeometryWS& g,
-                const BinningWS& b, const ImageWS& im, const int32_t* radii, cudaStream_t st);
+                const BinningWS& b, const ImageWS& im, const int32_t* radii, cudaStream_t st,
+                const TileOwner& own = TileOwner());
 int launch_render_fwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
-                      float* out_color, float* out_depth, cudaStream_t st);
+                      float* out_color, float* out_depth, cudaStream_t st, const TileOwner& own = TileOwner());
 int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
-                      const float* dL_dpix, float* acc, cudaStream_t st);
+                      const float* dL_dpix, float* acc, cudaStream_t st, const TileOwner& own = TileOwner());
 int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
                           const float* acc, const gsr_grads& gr, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
@@ -151,6 +162,12 @@ __device__ __forceinline__ uint32_t splat_subblock_mask(const float4 q0, const f
     if (fminf(q1v, q2v) <= thr) mask |= 1u << k;
   }
   return mask;
+}
+
+// n-th tile (row-major over the owned rows) of a rank that owns the tile rows ty = phase + k*stride
+__device__ __forceinline__ int owned_tile(int n, int gx, int stride, int phase) {
+  const int r = n / gx;
+  return (phase + r * stride) * gx + (n - r * gx);
 }
 
 // 128-bit streaming loads/stores

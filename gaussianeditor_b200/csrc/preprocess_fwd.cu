@@ -308,11 +308,15 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
       clamp_bits = (res[0] < 0 ? 1 : 0) | (res[1] < 0 ? 2 : 0) | (res[2] < 0 ? 4 : 0);
       rgb = make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
     }
-    rec.q2 = make_float4(rgb.x, rgb.y, rgb.z, 0.f);
+    // q2.w carries the radius and q1.z the view depth (= the depth-sort key bits): a record is self-contained, which
+    // is what lets the Gaussian-sharded path exchange the records alone (binning.cu: retouch_kernel)
+    rec.q2 = make_float4(rgb.x, rgb.y, rgb.z, __int_as_float(my_radius_i));
     float4* dst = reinterpret_cast<float4*>(a.records + idx);
     dst[0] = rec.q0;
     dst[1] = rec.q1;
     dst[2] = rec.q2;
+  } else if (live) {
+    reinterpret_cast<float4*>(a.records + idx)[2] = make_float4(0.f, 0.f, 0.f, 0.f);  // radius 0 = culled
   }
   if (live) {
     a.radii[idx] = my_radius_i;

@@ -37,6 +37,7 @@ struct BwdArgs {
   const uint32_t* n_contrib;
   const float* dL_dpix;
   float* acc;  // [P, ACC_STRIDE]
+  int own_stride, own_phase;  // tile-row ownership (1, 0 = all tiles)
 };
 
 // One (pixel, splat) hit. `ar` tracks the reference's accum_rec (backward.cu:515) dotted with dL_dpixel, updated
@@ -162,8 +163,9 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
   constexpr int PARTS = 8 / NSB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * BW_WARPS + warp;
-  const int tile = gw / PARTS, part = gw % PARTS;
-  if (tile >= ntiles) return;
+  const int part = gw % PARTS;
+  if (gw / PARTS >= ntiles) return;
+  const int tile = owned_tile(gw / PARTS, a.gx, a.own_stride, a.own_phase);  // ntiles counts the OWNED tiles
   float4(*stg)[32] = s_stage[warp];
   uint32_t* sid = s_id[warp];
 
@@ -302,8 +304,9 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
   constexpr int PARTS = 8 / NSB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gw = blockIdx.x * BW_WARPS + warp;
-  const int tile = gw / PARTS, part = gw % PARTS;
-  if (tile >= ntiles) return;
+  const int part = gw % PARTS;
+  if (gw / PARTS >= ntiles) return;
+  const int tile = owned_tile(gw / PARTS, a.gx, a.own_stride, a.own_phase);  // ntiles counts the OWNED tiles
   float4(*stg)[32] = s_stage[warp];
   uint32_t* sid = s_id[warp];
 
@@ -510,15 +513,17 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs 
 }  // namespace
 
 int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
-                      const float* dL_dpix, float* acc, cudaStream_t st) {
+                      const float* dL_dpix, float* acc, cudaStream_t st, const TileOwner& own) {
   BwdArgs a;
+  a.own_stride = own.stride; a.own_phase = own.phase;
   a.ranges = im.ranges; a.point_list = b.point_list; a.records = g.records; a.tile_last = im.tile_last;
   a.W = s.image_width; a.H = s.image_height;
   a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
   a.bg = s.bg; a.final_T = im.final_T; a.n_contrib = im.n_contrib; a.dL_dpix = dL_dpix; a.acc = acc;
-  const int ntiles = a.gx * a.gy;
+  const int ntiles = a.gx * own.owned_rows(a.gy);  // tiles this rank walks (all of them when own = {1,0})
   if (ntiles == 0) return GSR_OK;
-  const int v = g_opt.render_bwd_variant;
+  int v = g_opt.render_bwd_variant;
+  if (v == 0 && own.stride != 1) v = 4;  // the CTA-per-tile kernel maps blockIdx to tiles directly: single-GPU only
   if (v == 0) {
     render_bwd_cta_kernel<<<dim3(a.gx, a.gy), dim3(TILE, TILE), 0, st>>>(a);
   } else if (v == 2) {

@@ -1,0 +1,333 @@
+"""Gaussian-sharded multi-GPU rasterizer (BASELINE config 4).
+
+The reference has no multi-GPU rasterizer; this is the exact decomposition of the single-GPU pipeline over
+``world`` ranks, one process per GPU:
+
+  * rank g owns the Gaussians ``[g*L, g*L + n_g)`` (L = ceil(P/world)): parameters, optimizer state and the
+    per-Gaussian stages (preprocess forward, fused preprocess backward) stay on the owner;
+  * rank g owns the tile rows ``ty % world == g``: binning, blending and the blending backward run per tile owner;
+  * three collectives join the two decompositions (all on the compute stream, issued by ``torch.distributed``):
+      forward   ALL-GATHER   the 48-B splat records of every shard, in place (a record carries its radius and its
+                             depth key, so nothing else has to travel)
+                ALL-REDUCE   sum of the zero-initialised [4,H,W] frames (one writer per pixel: exact)
+      backward  REDUCE-SCATTER  the [P,12] 2-D gradient accumulators back to the index owners
+
+Because every P-sized array is indexed by GLOBAL Gaussian index, the gathered state equals the single-GPU state:
+images, radii, n_contrib and the per-tile lists are bit-identical to ``GaussianRasterizer`` on one GPU (asserted in
+tests/test_sharded.py); gradients agree to the usual float tolerance (the
+order of the atomic sums differs).
+
+The step functions (``shard_preprocess`` ... ``shard_backward_preprocess``) are thin wrappers of the C-ABI entry
+points and can also be driven for several *virtual* ranks on one GPU, which is how the single-GPU test covers the
+ownership logic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .rasterizer import (GaussianRasterizationSettings, _f32c, _geometry_bytes, _make_cloud, _make_settings,
+                         _pinned_i32, _ptr)
+
+ACC_STRIDE = 12  # floats per Gaussian in the 2-D gradient accumulators (csrc/common.cuh)
+
+
+class ShardPlan(NamedTuple):
+    """Index/tile ownership of one rank. ``P_total`` is the real cloud size, ``P_pad = slice_len * world`` the size
+    of every gathered array (the tail of the last slice is marked culled)."""
+    P_total: int
+    world: int
+    rank: int
+
+    @property
+    def slice_len(self) -> int:
+        return (self.P_total + self.world - 1) // self.world if self.P_total > 0 else 0
+
+    @property
+    def P_pad(self) -> int:
+        return self.slice_len * self.world
+
+    @property
+    def base(self) -> int:
+        return self.rank * self.slice_len
+
+    @property
+    def count(self) -> int:
+        """Number of real Gaussians this rank owns."""
+        return max(0, min(self.P_total, self.base + self.slice_len) - self.base)
+
+    def owned_tile_rows(self, H: int):
+        gy = (H + 15) // 16
+        return list(range(self.rank, gy, self.world))
+
+    def owner(self) -> "_lib.TileOwner":
+        return _lib.TileOwner(self.world, self.rank)
+
+
+def shard_slice(t: torch.Tensor, plan: ShardPlan) -> torch.Tensor:
+    """The rows of a full per-Gaussian tensor that `plan.rank` owns."""
+    return t[plan.base:plan.base + plan.count]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# collectives (backend-agnostic host logic; NCCL on GPUs, gloo in the CPU tests)
+# ---------------------------------------------------------------------------------------------------------
+def init_distributed(backend: str = "nccl", device: Optional[torch.device] = None):
+    """``init_process_group`` from the torchrun environment with the one setting this path needs.
+
+    ProcessGroupNCCL by default calls ``record_stream`` on every tensor a collective touches; the workspaces here are
+    several hundred MB, freed and re-allocated every step, and the deferred frees cost ~0.8 ms per step at config 3
+    (1.98 -> 1.13 ms measured on 2xB200). All collectives of this path are synchronous on the compute stream, so
+    stream recording is not needed: TORCH_NCCL_AVOID_RECORD_STREAMS=1 (must be set before the group is created)."""
+    import os
+    import torch.distributed as dist
+    os.environ.setdefault("TORCH_NCCL_AVOID_RECORD_STREAMS", "1")
+    if dist.is_initialized():
+        return
+    if backend == "nccl":
+        if device is None:
+            device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+        torch.cuda.set_device(device)
+        dist.init_process_group("nccl", device_id=device)
+    else:
+        dist.init_process_group(backend)
+
+
+
+class Exchange:
+    """The three collectives of the sharded path over a ``torch.distributed`` process group."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.backend = dist.get_backend(group)
+
+    def all_gather_inplace(self, total: torch.Tensor):
+        """`total` is [world * n, ...]; rank r has filled rows [r*n, (r+1)*n). On return every rank has all rows."""
+        n = total.shape[0] // self.world
+        mine = total[self.rank * n:(self.rank + 1) * n]
+        if self.backend == "nccl":
+            self.dist.all_gather_into_tensor(total, mine, group=self.group)  # in place: send buffer = own slot
+        else:  # gloo has no in-place flat all-gather
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            self.dist.all_gather(parts, mine.clone(), group=self.group)
+            for r, p in enumerate(parts):
+                total[r * n:(r + 1) * n].copy_(p)
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def reduce_scatter_sum(self, total: torch.Tensor, out: torch.Tensor):
+        """out[n, ...] = sum over ranks of total[rank*n:(rank+1)*n]."""
+        if self.backend == "nccl":
+            self.dist.reduce_scatter_tensor(out, total, op=self.dist.ReduceOp.SUM, group=self.group)
+        else:  # gloo: no reduce-scatter
+            tmp = total.clone()
+            self.dist.all_reduce(tmp, op=self.dist.ReduceOp.SUM, group=self.group)
+            n = out.shape[0]
+            out.copy_(tmp[self.rank * n:(self.rank + 1) * n])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# step functions = the C-ABI entry points
+# ---------------------------------------------------------------------------------------------------------
+class ShardBuffers:
+    """Per-rank device state of one sharded forward (all arrays indexed by global Gaussian index)."""
+    __slots__ = ("plan", "geom", "radii", "binning", "img", "R", "M", "W", "H", "inputs", "s", "own", "keep")
+
+
+def _view_bytes(base: torch.Tensor, ptr: int, nbytes: int) -> torch.Tensor:
+    off = ptr - base.data_ptr()
+    return base[off:off + nbytes]
+
+
+_rec_offset: dict = {}
+
+
+def exchange_view(buf: ShardBuffers) -> torch.Tensor:
+    """The splat records [P_pad, 48] (uint8 view onto the geometry workspace): the one array that is exchanged."""
+    P = buf.plan.P_pad
+    off = _rec_offset.get(P)
+    if off is None:
+        v = _lib.ExchangeView()
+        _lib.check(_lib.load().gsr_view_exchange(_ptr(buf.geom), P, C.byref(v)), "gsr_view_exchange")
+        off = _rec_offset[P] = v.records - buf.geom.data_ptr()
+    return buf.geom[off:off + P * 48].view(P, 48)
+
+
+def shard_preprocess(plan: ShardPlan, rs: GaussianRasterizationSettings, means3D, sh, colors_precomp, opacities,
+                     scales, rotations, cov3Ds_precomp, *, geom: Optional[torch.Tensor] = None,
+                     radii: Optional[torch.Tensor] = None) -> ShardBuffers:
+    """Stage 1: project this rank's Gaussians into its slice of the global arrays. `geom` / `radii` may be passed
+    in to share one set of global arrays between virtual ranks of a single process."""
+    lib = _lib.load()
+    if not means3D.is_cuda:
+        raise RuntimeError("the B200 rasterizer needs CUDA tensors (there is no CPU path)")
+    if means3D.size(0) != plan.count:
+        raise RuntimeError(f"rank {plan.rank} owns {plan.count} Gaussians, got {means3D.size(0)}")
+    device = means3D.device
+    H, W = int(rs.image_height), int(rs.image_width)
+    M = sh.size(1) if sh.numel() != 0 else 0
+    buf = ShardBuffers()
+    buf.plan, buf.M, buf.W, buf.H = plan, M, W, H
+    with torch.cuda.device(device):
+        means3D = _f32c(means3D, device); opacities = _f32c(opacities, device)
+        sh = _f32c(sh, device); colors_precomp = _f32c(colors_precomp, device)
+        scales = _f32c(scales, device); rotations = _f32c(rotations, device)
+        cov3Ds_precomp = _f32c(cov3Ds_precomp, device)
+        buf.inputs = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        gbytes = _geometry_bytes(lib, plan.P_pad)
+        buf.geom = geom if geom is not None else torch.empty(gbytes, dtype=torch.uint8, device=device)
+        buf.radii = radii if radii is not None else torch.empty(plan.P_pad, dtype=torch.int32, device=device)
+        buf.keep = []
+        s = buf.s = _make_settings(rs, M, device, buf.keep)   # one settings struct for all five stage calls
+        buf.own = plan.owner()
+        c = _make_cloud(plan.count, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.gsr_shard_preprocess(C.byref(s), C.byref(c), plan.P_pad, plan.base, plan.slice_len,
+                                            _ptr(buf.geom), gbytes, _ptr(buf.radii), st), "gsr_shard_preprocess")
+    return buf
+
+
+def shard_order(buf: ShardBuffers) -> int:
+    """Stage 2 (after the all-gather): radii of all Gaussians, owned-tile counts, depth order, scan. Returns this
+    rank's instance count (one stream synchronisation to read it)."""
+    lib = _lib.load()
+    device = buf.geom.device
+    with torch.cuda.device(device):
+        s, own = buf.s, buf.own
+        stream = torch.cuda.current_stream(device)
+        pinned = _pinned_i32(device)
+        _lib.check(lib.gsr_shard_order(C.byref(s), C.byref(own), buf.plan.P_pad, _ptr(buf.geom), buf.geom.numel(),
+                                       _ptr(buf.radii), C.c_void_p(pinned.data_ptr()),
+                                       C.c_void_p(stream.cuda_stream)), "gsr_shard_order")
+        stream.synchronize()
+        buf.R = int(pinned[0])
+    return buf.R
+
+
+def shard_render(buf: ShardBuffers, color: torch.Tensor, depth: torch.Tensor):
+    """Stage 3: bin + blend the owned tiles into `color` [3,H,W] / `depth` [1,H,W] (zero elsewhere: caller zero-fills)."""
+    lib = _lib.load()
+    device = buf.geom.device
+    with torch.cuda.device(device):
+        s, own = buf.s, buf.own
+        P, R, W, H = buf.plan.P_pad, buf.R, buf.W, buf.H
+        u8 = dict(dtype=torch.uint8, device=device)
+        bbytes = lib.gsr_binning_bytes(P, R, W, H) if R > 0 else 0
+        buf.binning = torch.empty(bbytes, **u8)
+        ibytes = lib.gsr_image_bytes(W, H)
+        buf.img = torch.empty(ibytes, **u8)
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.gsr_shard_render(C.byref(s), C.byref(own), P, R, _ptr(buf.geom), buf.geom.numel(),
+                                        _ptr(buf.binning), bbytes, _ptr(buf.img), ibytes, _ptr(buf.radii),
+                                        _ptr(color), _ptr(depth), st), "gsr_shard_render")
+
+
+def shard_backward_render(buf: ShardBuffers, grad_out_color: torch.Tensor) -> torch.Tensor:
+    """Backward stage 1: this rank's tiles -> partial accumulators [P_pad, 12] (zero for untouched Gaussians)."""
+    lib = _lib.load()
+    device = buf.geom.device
+    with torch.cuda.device(device):
+        s, own = buf.s, buf.own
+        grad_out_color = _f32c(grad_out_color, device)
+        acc = torch.empty(buf.plan.P_pad, ACC_STRIDE, dtype=torch.float32, device=device)
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.gsr_shard_backward_render(C.byref(s), C.byref(own), buf.plan.P_pad, buf.R, _ptr(buf.geom),
+                                                 buf.geom.numel(), _ptr(buf.binning), buf.binning.numel(),
+                                                 _ptr(buf.img), buf.img.numel(), _ptr(grad_out_color), _ptr(acc),
+                                                 acc.numel() * 4, st), "gsr_shard_backward_render")
+    return acc
+
+
+def shard_backward_preprocess(buf: ShardBuffers, acc_slice: torch.Tensor):
+    """Backward stage 2 (after the reduce-scatter): gradients of this rank's Gaussians, reference slot order."""
+    lib = _lib.load()
+    device = buf.geom.device
+    plan, M = buf.plan, buf.M
+    n = plan.count
+    (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp) = buf.inputs
+    with torch.cuda.device(device):
+        f32 = dict(dtype=torch.float32, device=device)
+        dL_dmeans3D = torch.empty(n, 3, **f32); dL_dmeans2D = torch.empty(n, 3, **f32)
+        dL_dcolors = torch.empty(n, 3, **f32); dL_dopacity = torch.empty(n, 1, **f32)
+        dL_dcov3D = torch.empty(n, 6, **f32); dL_dsh = torch.empty(n, M, 3, **f32)
+        dL_dscales = torch.empty(n, 3, **f32); dL_drotations = torch.empty(n, 4, **f32)
+        if n > 0:
+            s = buf.s
+            c = _make_cloud(n, means3D, opacities, sh, colors_precomp, scales, rotations, cov3Ds_precomp)
+            gr = _lib.Grads(_ptr(dL_dmeans3D), _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity),
+                            _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
+            st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+            _lib.check(lib.gsr_shard_backward_preprocess(C.byref(s), C.byref(c), plan.P_pad, plan.base, _ptr(buf.geom),
+                                                         buf.geom.numel(), _ptr(buf.radii), _ptr(acc_slice),
+                                                         C.byref(gr), st), "gsr_shard_backward_preprocess")
+            if scales.numel() == 0:
+                dL_dscales.zero_(); dL_drotations.zero_()
+    return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# autograd + module (one process per GPU)
+# ---------------------------------------------------------------------------------------------------------
+class _ShardedRasterize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, plan,
+                exchange):
+        buf = shard_preprocess(plan, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+        exchange.all_gather_inplace(exchange_view(buf))
+        shard_order(buf)
+        frame = torch.zeros(4, buf.H, buf.W, dtype=torch.float32, device=means3D.device)
+        shard_render(buf, frame[:3], frame[3:])
+        exchange.all_reduce_sum(frame)
+        ctx.buf, ctx.exchange = buf, exchange
+        radii = shard_slice(buf.radii, plan)
+        ctx.mark_non_differentiable(radii)
+        _ShardedRasterize.last_buffers = buf  # parity tests / instrumentation only
+        return frame[:3], radii, frame[3:]
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        buf, exchange = ctx.buf, ctx.exchange
+        acc = shard_backward_render(buf, grad_out_color)
+        acc_slice = torch.empty(buf.plan.slice_len, ACC_STRIDE, dtype=torch.float32, device=acc.device)
+        exchange.reduce_scatter_sum(acc, acc_slice)
+        grads = shard_backward_preprocess(buf, acc_slice)
+        return (*grads, None, None, None)
+
+
+class ShardedGaussianRasterizer(nn.Module):
+    """``GaussianRasterizer`` for a cloud sharded by Gaussian index over the ranks of a process group.
+
+    ``forward`` takes THIS RANK's rows of the per-Gaussian tensors (``shard_slice(full, plan)``) and returns the
+    full image on every rank plus the radii of this rank's Gaussians; gradients flow to the local rows.
+    """
+
+    def __init__(self, raster_settings: GaussianRasterizationSettings, P_total: int, group=None):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.exchange = Exchange(group)
+        self.plan = ShardPlan(int(P_total), self.exchange.world, self.exchange.rank)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (
+                (scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.empty(0, dtype=torch.float32, device=means3D.device)
+        shs = empty if shs is None else shs
+        colors_precomp = empty if colors_precomp is None else colors_precomp
+        scales = empty if scales is None else scales
+        rotations = empty if rotations is None else rotations
+        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        return _ShardedRasterize.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                       cov3D_precomp, self.raster_settings, self.plan, self.exchange)

@@ -39,7 +39,7 @@ extern "C" {
 #define GSR_ERR_CUDA (-2)    /* CUDA runtime error; message in gsr_last_error() */
 #define GSR_ERR_WORKSPACE (-3) /* a workspace is smaller than the matching gsr_*_bytes() query */
 
-#define GSR_ABI_VERSION 1
+#define GSR_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define GSR_API __attribute__((visibility("default")))
@@ -171,6 +171,52 @@ GSR_API int gsr_view_geometry(const void* geometry, int32_t P, gsr_geometry_view
 GSR_API int gsr_view_binning(const void* binning, int32_t P, int64_t num_rendered, int32_t image_width,
                      int32_t image_height, gsr_binning_view* out);
 GSR_API int gsr_view_image(const void* image, int32_t image_width, int32_t image_height, gsr_image_view* out);
+
+/* ---- Gaussian-sharded multi-GPU path (BASELINE config 4) ----------------------------------
+ * The reference has no multi-GPU rasterizer; these entry points split the single-GPU pipeline at the two places
+ * where the Gaussian-index decomposition (preprocess, fused preprocess backward) meets the tile decomposition
+ * (binning, blending), so that a host can put one collective in each gap:
+ *
+ *   rank g owns Gaussians [index_base, index_base + shard.P) of P_total and the tile rows ty % row_stride == row_phase.
+ *   forward : gsr_shard_preprocess  -> ALL-GATHER of the 48-byte splat records (gsr_view_exchange gives the array;
+ *                                      a record carries its radius and depth key, so it is the whole exchange)
+ *             gsr_shard_order       -> radii of all Gaussians, owned-tile counts, depth order, scan, num_rendered
+ *                                      (this rank's instances)
+ *             gsr_shard_render      -> binning + blending of the owned tiles into zero-initialised full frames
+ *                                      -> ALL-REDUCE(sum) of the frames (every pixel has exactly one non-zero
+ *                                         contributor, so the sum is a bit-exact concatenation)
+ *   backward: gsr_shard_backward_render     -> partial 2-D gradient accumulators [P_total, 12]
+ *                                              -> REDUCE-SCATTER(sum) to the index owners
+ *             gsr_shard_backward_preprocess -> gradients of this rank's Gaussians
+ * All P_total-sized arrays (geometry workspace, radii, accumulators) are indexed by GLOBAL Gaussian index, so
+ * the gathered state is exactly the single-GPU state and the images are bit-identical to gsr_forward_render's.
+ * Every rank must pass the same P_total and slice_len (= ceil(P_total / world)); slots of a slice beyond
+ * shard.P are marked culled. */
+typedef struct gsr_tile_owner {
+  int32_t row_stride; /* >= 1 */
+  int32_t row_phase;  /* 0 .. row_stride-1 */
+} gsr_tile_owner;
+typedef struct gsr_exchange_view {
+  void* records; /* [P_total] 48-byte splat records; rank g writes [g*slice_len, (g+1)*slice_len) */
+} gsr_exchange_view;
+GSR_API int gsr_view_exchange(void* geometry, int32_t P_total, gsr_exchange_view* out);
+GSR_API int gsr_shard_preprocess(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
+                         int32_t slice_len, void* geometry, size_t geometry_bytes, int32_t* radii_total, void* stream);
+/* radii_total [P_total] is (re)written here for ALL Gaussians from the gathered records. */
+GSR_API int gsr_shard_order(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total, void* geometry,
+                    size_t geometry_bytes, int32_t* radii_total, int32_t* num_rendered_host, void* stream);
+GSR_API int gsr_shard_render(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total, int32_t num_rendered,
+                     void* geometry, size_t geometry_bytes, void* binning, size_t binning_bytes, void* image,
+                     size_t image_bytes, const int32_t* radii_total, float* out_color, float* out_depth, void* stream);
+GSR_API int gsr_shard_backward_render(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total,
+                              int32_t num_rendered, const void* geometry, size_t geometry_bytes, const void* binning,
+                              size_t binning_bytes, const void* image, size_t image_bytes, const float* dL_dout_color,
+                              void* acc_total, size_t acc_bytes, void* stream);
+/* acc_slice: this rank's [shard.P, 12] rows of the reduced accumulators (gsr_backward_scratch_bytes(shard.P)). */
+GSR_API int gsr_shard_backward_preprocess(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total,
+                                  int32_t index_base, const void* geometry, size_t geometry_bytes,
+                                  const int32_t* radii_total, const void* acc_slice, const gsr_grads* grads,
+                                  void* stream);
 
 /* ---- tuning / instrumentation ---------------------------------------------------------------------------
  * gsr_set_option("render_variant", v) etc.; unknown names return GSR_ERR_INVALID.

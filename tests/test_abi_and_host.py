@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/gsr_b200.h but not exported"
     assert sorted(_lib.SYMBOLS) == syms
-    assert lib.gsr_abi_version() == 1
+    assert lib.gsr_abi_version() == 2
 
 
 def test_library_contains_sm100a_code_and_tma():

@@ -1,0 +1,176 @@
+"""Gaussian-sharded multi-GPU path (gaussianeditor_b200/sharded.py, BASELINE config 4).
+
+CPU (not gpu): shard plan arithmetic and the three collectives under gloo, world_size 2.
+GPU: (a) the ownership logic of the kernels with VIRTUAL ranks on one device -- per-rank images must tile the
+single-GPU image bit-exactly and the summed accumulators must reproduce its gradients; (b) the real thing, one
+process per GPU over NCCL (needs >= 2 GPUs, skipped otherwise).
+"""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gaussianeditor_b200 import sharded as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def test_shard_plan_partitions_indices_and_tile_rows():
+    for P in (1, 7, 100, 1001, 5_000_000):
+        for w in (1, 2, 3, 4, 8):
+            plans = [S.ShardPlan(P, w, r) for r in range(w)]
+            assert all(p.slice_len == plans[0].slice_len and p.P_pad == plans[0].P_pad for p in plans)
+            assert plans[0].P_pad >= P and plans[0].P_pad - P < w
+            covered = []
+            for p in plans:
+                assert 0 <= p.count <= p.slice_len
+                covered += list(range(p.base, p.base + p.count)) if P <= 1001 else []
+            assert sum(p.count for p in plans) == P
+            if P <= 1001:
+                assert covered == list(range(P))
+            for H in (16, 17, 1080, 1200):
+                rows = sorted(r for p in plans for r in p.owned_tile_rows(H))
+                assert rows == list(range((H + 15) // 16))
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ex = S.Exchange()
+        plan = S.ShardPlan(11, world, rank)
+        n, Pp = plan.slice_len, plan.P_pad
+        # all-gather in place: every rank fills its own slice of [P_pad, 48] bytes / [P_pad] keys
+        rec = torch.zeros(Pp, 48, dtype=torch.uint8)
+        rec[plan.base:plan.base + n] = (torch.arange(n * 48, dtype=torch.int64).view(n, 48) % 251 + rank).to(torch.uint8)
+        ex.all_gather_inplace(rec)
+        ok = True
+        for r in range(world):
+            want = (torch.arange(n * 48, dtype=torch.int64).view(n, 48) % 251 + r).to(torch.uint8)
+            ok &= bool((rec[r * n:(r + 1) * n] == want).all())
+        # frame all-reduce: every pixel has one writer (tile rows interleaved) -> sum == concatenation, bit for bit
+        H, W = 40, 8
+        g = torch.Generator().manual_seed(5)
+        full = torch.randn(4, H, W, generator=g)
+        frame = torch.zeros(4, H, W)
+        for ty in plan.owned_tile_rows(H):
+            frame[:, 16 * ty:16 * ty + 16] = full[:, 16 * ty:16 * ty + 16]
+        ex.all_reduce_sum(frame)
+        ok &= torch.equal(frame, full)
+        # reduce-scatter of the accumulators
+        acc = torch.full((Pp, S.ACC_STRIDE), float(rank + 1))
+        mine = torch.empty(n, S.ACC_STRIDE)
+        ex.reduce_scatter_sum(acc, mine)
+        ok &= bool((mine == float(sum(range(1, world + 1)))).all())
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_exchange_collectives():
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_gloo_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert [out[r] for r in range(world)] == [True] * world
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------------------
+_CASE = {}
+
+
+def _case():
+    """Cloud, camera, dL and the single-GPU result, computed once for all world sizes."""
+    if not _CASE:
+        from gaussianeditor_b200 import synth
+        from util import run_ours
+        cloud, cams = synth.make_config("c3", P=60013)  # P not divisible by the world sizes: exercises the padded tail
+        cam = cams[0]
+        bg = (0.2, 0.5, 0.1)
+        dL = np.random.default_rng(3).random((3, cam.image_height, cam.image_width), dtype=np.float32)
+        _CASE.update(cloud=cloud, cam=cam, bg=bg, dL=dL, ref=run_ours(cloud, cam, bg=bg, dL=dL))
+    return _CASE
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_virtual_ranks_tile_the_single_gpu_result(world):
+    """Drive the sharded C-ABI for `world` virtual ranks on one GPU (the all-gather is a shared buffer, the
+    all-reduce / reduce-scatter are explicit sums) and compare with the single-GPU rasterizer."""
+    from util import cloud_tensors, settings_from, rel_l2
+    dev = torch.device("cuda")
+    case = _case()
+    cloud, cam, bg, dL, ref = case["cloud"], case["cam"], case["bg"], case["dL"], case["ref"]
+    H, W = cam.image_height, cam.image_width
+    rs = settings_from(cam, bg, cloud.sh_degree, dev)
+    full = cloud_tensors(cloud, dev)
+    P = cloud.means3D.shape[0]
+    empty = torch.empty(0, device=dev)
+    plans = [S.ShardPlan(P, world, r) for r in range(world)]
+    # stage 1 on every rank into ONE set of global arrays == the state after the all-gather
+    geom = radii = None
+    bufs = []
+    for p in plans:
+        sl = lambda t: S.shard_slice(t, p)
+        b = S.shard_preprocess(p, rs, sl(full["means3D"]), sl(full["shs"]), empty, sl(full["opacities"]),
+                               sl(full["scales"]), sl(full["rotations"]), empty, geom=geom, radii=radii)
+        geom, radii = b.geom, b.radii
+        bufs.append(b)
+    assert torch.equal(radii[:P], ref["radii"])
+    for b in bufs:  # each rank continues on its own copy, as after a real all-gather (radii are rebuilt from the records)
+        b.geom = geom.clone(); b.radii = torch.full_like(radii, -7)
+    frames, accs, Rs = [], [], []
+    gdL = torch.from_numpy(dL).to(dev)
+    for b in bufs:
+        Rs.append(S.shard_order(b))
+        frame = torch.zeros(4, H, W, device=dev)
+        S.shard_render(b, frame[:3], frame[3:])
+        frames.append(frame)
+        accs.append(S.shard_backward_render(b, gdL))
+    assert sum(Rs) == ref["R"]
+    assert all(torch.equal(b.radii[:P], ref["radii"]) and int(b.radii[P:].abs().sum()) == 0 for b in bufs)
+    # every pixel is written by exactly one rank, rows interleaved by tile row
+    total = torch.stack(frames).sum(0)
+    assert torch.equal(total[:3], ref["color"]) and torch.equal(total[3:], ref["depth"])
+    for r, f in enumerate(frames):
+        rows = torch.zeros(H, dtype=torch.bool, device=dev)
+        for ty in plans[r].owned_tile_rows(H):
+            rows[16 * ty:16 * ty + 16] = True
+        assert float(f[:, ~rows].abs().sum()) == 0.0
+        assert torch.equal(f[:3][:, rows], ref["color"][:, rows])
+    acc = torch.stack(accs).sum(0)
+    names = ["dmean3D", "dmean2D", "dsh", None, "dopacity", "dscale", "drot", None]
+    for b in bufs:
+        p = b.plan
+        grads = S.shard_backward_preprocess(b, acc[p.base:p.base + p.slice_len].contiguous())
+        for name, g in zip(names, grads):
+            if name is None:
+                continue
+            want = ref["grads"][name][p.base:p.base + p.count]
+            assert g.shape == want.shape
+            assert rel_l2(g.cpu().numpy(), want.cpu().numpy()) <= 2e-5, (name, p.rank)
+
+
+@pytest.mark.gpu
+def test_two_process_nccl_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "sharded_check.py"), "--config", "c3",
+           "--P", "30001"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SHARDED_CHECK_OK" in r.stdout
