@@ -23,6 +23,7 @@ SYMBOLS = [
     "gsr_host_upload_cloud", "gsr_host_step",
     "gsr_view_exchange", "gsr_shard_preprocess", "gsr_shard_order", "gsr_shard_render", "gsr_shard_backward_render",
     "gsr_shard_backward_preprocess",
+    "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close", "gsr_peer_free", "gsr_shard_preprocess_p2p",
 ]
 
 
@@ -140,6 +141,12 @@ def load():
     lib.gsr_shard_backward_render.argtypes = [S, TO, i32, i32, vp, sz, vp, sz, vp, sz, vp, vp, sz, vp]
     lib.gsr_shard_backward_preprocess.restype = C.c_int
     lib.gsr_shard_backward_preprocess.argtypes = [S, Cl, i32, i32, vp, sz, vp, vp, C.POINTER(Grads), vp]
+    lib.gsr_peer_alloc.restype = C.c_int; lib.gsr_peer_alloc.argtypes = [sz, C.POINTER(vp), vp]
+    lib.gsr_peer_open.restype = C.c_int; lib.gsr_peer_open.argtypes = [vp, C.POINTER(vp)]
+    lib.gsr_peer_close.restype = C.c_int; lib.gsr_peer_close.argtypes = [vp]
+    lib.gsr_peer_free.restype = C.c_int; lib.gsr_peer_free.argtypes = [vp]
+    lib.gsr_shard_preprocess_p2p.restype = C.c_int
+    lib.gsr_shard_preprocess_p2p.argtypes = [S, Cl, i32, i32, i32, C.POINTER(vp), i32, i32, sz, vp, vp]
     if lib.gsr_abi_version() != 2:
         raise RuntimeError("libgsr_b200.so ABI version mismatch")
     _lib = lib

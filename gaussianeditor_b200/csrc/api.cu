@@ -288,6 +288,70 @@ int gsr_shard_preprocess(const gsr_settings* s, const gsr_cloud* shard, int32_t 
   return GSR_OK;
 }
 
+int gsr_peer_alloc(size_t bytes, void** ptr_out, void* handle_out) {
+  if (!ptr_out || !handle_out || bytes == 0) { set_error("peer_alloc: bad arguments"); return GSR_ERR_INVALID; }
+  static_assert(sizeof(cudaIpcMemHandle_t) <= GSR_PEER_HANDLE_BYTES, "IPC handle size");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return check_cuda(e, "peer_alloc cudaMalloc");
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return check_cuda(e, "cudaIpcGetMemHandle"); }
+  memset(handle_out, 0, GSR_PEER_HANDLE_BYTES);
+  memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return GSR_OK;
+}
+int gsr_peer_open(const void* handle, void** ptr_out) {
+  if (!handle || !ptr_out) { set_error("peer_open: bad arguments"); return GSR_ERR_INVALID; }
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return check_cuda(e, "cudaIpcOpenMemHandle");
+  *ptr_out = p;
+  return GSR_OK;
+}
+int gsr_peer_close(void* ptr) { return ptr ? check_cuda(cudaIpcCloseMemHandle(ptr), "cudaIpcCloseMemHandle") : GSR_OK; }
+int gsr_peer_free(void* ptr) { return ptr ? check_cuda(cudaFree(ptr), "peer_free") : GSR_OK; }
+
+int gsr_shard_preprocess_p2p(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
+                             int32_t slice_len, void* const* peer_geometry, int32_t world, int32_t rank,
+                             size_t geometry_bytes, int32_t* radii_total, void* stream) {
+  int rc = validate(s, shard);
+  if (rc) return rc;
+  if (world < 1 || world > GSR_MAX_PEERS || rank < 0 || rank >= world || !peer_geometry) {
+    set_error("p2p preprocess: need 1 <= world <= %d, 0 <= rank < world", GSR_MAX_PEERS);
+    return GSR_ERR_INVALID;
+  }
+  if (P_total <= 0 || index_base < 0 || slice_len < shard->P || (int64_t)index_base + slice_len > P_total) {
+    set_error("shard [%d, %d+%d) (P=%d) does not fit P_total=%d", index_base, index_base, slice_len, shard->P, P_total);
+    return GSR_ERR_INVALID;
+  }
+  if (!radii_total) { set_error("radii is null"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  GeometryWS g;  // own workspace: everything but the records is local
+  if (!peer_geometry[rank] || !carve_geometry(peer_geometry[rank], P_total, g)) return GSR_ERR_CUDA;
+  if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
+  SplatRecord* dst[GSR_MAX_PEERS];
+  for (int r = 0; r < world; r++) {
+    GeometryWS gr;
+    if (!peer_geometry[r] || !carve_geometry(peer_geometry[r], P_total, gr)) { set_error("peer workspace %d is null", r); return GSR_ERR_INVALID; }
+    dst[r] = gr.records + index_base;
+  }
+  StageScope t(ST_PRE_FWD, st);
+  if (shard->P > 0) {
+    rc = launch_preprocess_fwd(*s, *shard, slice_geometry(g, index_base), radii_total + index_base, st, dst, world);
+    if (rc) return rc;
+  }
+  const int pad = slice_len - shard->P;
+  for (int r = 0; pad > 0 && r < world; r++) {
+    cudaError_t e = cudaMemsetAsync(dst[r] + shard->P, 0, (size_t)pad * sizeof(SplatRecord), st);
+    if (e != cudaSuccess) return check_cuda(e, "slice padding");
+  }
+  return GSR_OK;
+}
+
 int gsr_shard_order(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total, void* geometry,
                     size_t geometry_bytes, int32_t* radii_total, int32_t* num_rendered_host, void* stream) {
   int rc = check_settings(s);

@@ -96,8 +96,9 @@ int check_cuda(cudaError_t e, const char* what);
 int check_launch(const char* what, bool debug, cudaStream_t st);
 
 // ---- stage entry points (host side; each file owns its kernels) ------------------------------------------
+// peer_records/npeers: fused all-gather of the sharded path (every rank's view of this shard's record slice), else 0
 int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
-                          cudaStream_t st);
+                          cudaStream_t st, SplatRecord* const* peer_records = nullptr, int npeers = 0);
 int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
                              bool debug);
 // Sharded path: recompute tiles_touched (owned tile rows only) and the sort identity for all P gathered Gaussians.

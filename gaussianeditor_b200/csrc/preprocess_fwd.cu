@@ -50,6 +50,10 @@ struct PreArgs {
   uint32_t* depth_keys;
   uint32_t* ident;
   int32_t* radii;
+  // Fused all-gather of the Gaussian-sharded path (P2P kernel variant): the CTA's block of records is pushed with one
+  // TMA bulk store per destination into the records array of every rank (own copy included) over NVLink peer memory.
+  SplatRecord* peer_records[GSR_MAX_PEERS];  // pointers to THIS shard's slice inside each rank's records array
+  int npeers;
 };
 
 // SH basis weights of forward.cu:30-61 for the unit view direction (x,y,z), pinned to the operation sequence nvcc emits
@@ -101,9 +105,10 @@ __device__ __forceinline__ float sh_channel(int deg, const float* w, ShFn sh) {
   return __fadd_rn(res, 0.5f);
 }
 
-template <bool BULK_SH>
+template <bool BULK_SH, bool P2P = false>
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreArgs a) {
   __shared__ __align__(16) float sh_rows[BULK_SH ? PRE_THREADS * SH_ROW_WORDS : 4];
+  __shared__ __align__(128) float4 s_rec[P2P ? PRE_THREADS * 3 : 1];  // the CTA's records, contiguous like in HBM
   __shared__ uint64_t bar;
 
   const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
@@ -311,12 +316,30 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     // q2.w carries the radius and q1.z the view depth (= the depth-sort key bits): a record is self-contained, which
     // is what lets the Gaussian-sharded path exchange the records alone (binning.cu: retouch_kernel)
     rec.q2 = make_float4(rgb.x, rgb.y, rgb.z, __int_as_float(my_radius_i));
-    float4* dst = reinterpret_cast<float4*>(a.records + idx);
+    float4* dst = P2P ? &s_rec[threadIdx.x * 3] : reinterpret_cast<float4*>(a.records + idx);
     dst[0] = rec.q0;
     dst[1] = rec.q1;
     dst[2] = rec.q2;
   } else if (live) {
-    reinterpret_cast<float4*>(a.records + idx)[2] = make_float4(0.f, 0.f, 0.f, 0.f);  // radius 0 = culled
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);  // radius 0 = culled
+    if (P2P) {
+      s_rec[threadIdx.x * 3] = z; s_rec[threadIdx.x * 3 + 1] = z; s_rec[threadIdx.x * 3 + 2] = z;
+    } else {
+      reinterpret_cast<float4*>(a.records + idx)[2] = z;
+    }
+  }
+  if (P2P) {
+    // compute -> collective in one kernel: the block of records goes straight from shared memory to every rank's
+    // records array (TMA bulk stores over NVLink peer mappings; one elected thread per destination)
+    fence_proxy_async_smem();
+    __syncthreads();
+    const int first = blockIdx.x * PRE_THREADS;
+    const uint32_t bytes = (uint32_t)(min(PRE_THREADS, a.P - first) * (int)sizeof(SplatRecord));
+    if ((int)threadIdx.x < a.npeers) {
+      bulk_s2g(a.peer_records[threadIdx.x] + first, s_rec, bytes);
+      bulk_commit();
+      bulk_wait_read0();  // shared memory must stay intact until the TMA unit has read it
+    }
   }
   if (live) {
     a.radii[idx] = my_radius_i;
@@ -339,8 +362,10 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 }  // namespace
 
 int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
-                          cudaStream_t st) {
+                          cudaStream_t st, SplatRecord* const* peer_records, int npeers) {
   PreArgs a;
+  a.npeers = npeers;
+  for (int i = 0; i < GSR_MAX_PEERS; i++) a.peer_records[i] = i < npeers ? peer_records[i] : nullptr;
   a.P = c.P; a.D = s.sh_degree; a.M = s.sh_coeffs; a.W = s.image_width; a.H = s.image_height;
   a.gx = (a.W + TILE - 1) / TILE; a.gy = (a.H + TILE - 1) / TILE;
   a.tan_fovx = s.tanfovx; a.tan_fovy = s.tanfovy;
@@ -357,7 +382,12 @@ int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const Geome
   const bool bulk = g_opt.preprocess_variant >= 1 && c.colors_precomp == nullptr && c.shs != nullptr &&
                     (s.sh_coeffs * 12) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.shs) % 16) == 0 &&
                     (s.sh_coeffs * 12) <= 192;
-  if (bulk)
+  if (npeers > 0) {
+    if (bulk)
+      preprocess_fwd_kernel<true, true><<<grid, PRE_THREADS, 0, st>>>(a);
+    else
+      preprocess_fwd_kernel<false, true><<<grid, PRE_THREADS, 0, st>>>(a);
+  } else if (bulk)
     preprocess_fwd_kernel<true><<<grid, PRE_THREADS, 0, st>>>(a);
   else
     preprocess_fwd_kernel<false><<<grid, PRE_THREADS, 0, st>>>(a);

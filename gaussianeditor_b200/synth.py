@@ -194,3 +194,34 @@ def make_config(name: str, P: int | None = None):
     if name == "c5":
         return bicycle_cloud(P, 5, size=0.5), ring_cameras(48, 2.25, 15.0, W, H, 61.0)
     raise KeyError(name)
+
+
+def make_config_cached(name: str, P: int | None = None, cache_dir: str = "/tmp"):
+    """make_config with the cloud cached as .npy files under `cache_dir` (multi-process benches: the 5M-Gaussian cloud
+    takes ~45 s to generate; ranks other than the first to arrive just load it). Cameras are always recomputed."""
+    import os
+    import time
+    tag = f"gsr_synth_{name}_{CONFIGS[name]['P'] if P is None else P}"
+    done = os.path.join(cache_dir, tag + ".done")
+    lock = os.path.join(cache_dir, tag + ".lock")
+    fields = ["means3D", "scales", "rotations", "opacities", "shs"]
+    cams = None
+    if not os.path.exists(done):
+        try:
+            fd = os.open(lock, os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+            os.close(fd)
+            cloud, cams = make_config(name, P)
+            for f in fields:
+                np.save(os.path.join(cache_dir, f"{tag}_{f}.npy"), getattr(cloud, f))
+            with open(done, "w") as fh:
+                fh.write(str(cloud.sh_degree))
+            return cloud, cams
+        except FileExistsError:
+            while not os.path.exists(done):
+                time.sleep(0.5)
+    with open(done) as fh:
+        deg = int(fh.read())
+    arrs = {f: np.load(os.path.join(cache_dir, f"{tag}_{f}.npy")) for f in fields}
+    c = CONFIGS[name]
+    small = make_config(name, 16)[1]  # cameras do not depend on P
+    return Cloud(sh_degree=deg, **arrs), small

@@ -218,6 +218,24 @@ GSR_API int gsr_shard_backward_preprocess(const gsr_settings* s, const gsr_cloud
                                   const int32_t* radii_total, const void* acc_slice, const gsr_grads* grads,
                                   void* stream);
 
+/* ---- fused preprocess + all-gather over NVLink peer memory ---------------------------------------------------
+ * Instead of gsr_shard_preprocess followed by an all-gather, every rank's preprocess kernel pushes its block of
+ * records into the geometry workspace of EVERY rank (TMA bulk stores from shared memory to peer-mapped global
+ * memory). The workspaces must come from gsr_peer_alloc and be opened on the other ranks with gsr_peer_open:
+ * peer_geometry[r] is rank r's workspace as mapped in THIS process (own entry = the local pointer), all of the same
+ * size and therefore the same layout. The caller must run a cross-rank barrier on `stream` (e.g. a 4-byte
+ * all-reduce) between this call and gsr_shard_order, and between a rank's last read of a workspace and the next
+ * gsr_shard_preprocess_p2p that targets it (any collective of the step does). */
+#define GSR_MAX_PEERS 8
+#define GSR_PEER_HANDLE_BYTES 64
+GSR_API int gsr_peer_alloc(size_t bytes, void** ptr_out, void* handle_out /* [GSR_PEER_HANDLE_BYTES] host */);
+GSR_API int gsr_peer_open(const void* handle /* [GSR_PEER_HANDLE_BYTES] host */, void** ptr_out);
+GSR_API int gsr_peer_close(void* ptr);
+GSR_API int gsr_peer_free(void* ptr);
+GSR_API int gsr_shard_preprocess_p2p(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
+                             int32_t slice_len, void* const* peer_geometry /* [world] host array */, int32_t world,
+                             int32_t rank, size_t geometry_bytes, int32_t* radii_total, void* stream);
+
 /* ---- tuning / instrumentation ---------------------------------------------------------------------------
  * gsr_set_option("render_variant", v) etc.; unknown names return GSR_ERR_INVALID.
  * gsr_launch_count(): number of this library's kernel launches (CUB's included) since process start. */

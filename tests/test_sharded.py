@@ -165,12 +165,13 @@ def test_virtual_ranks_tile_the_single_gpu_result(world):
 
 
 @pytest.mark.gpu
-def test_two_process_nccl_matches_single_gpu():
+@pytest.mark.parametrize("p2p", [False, True])
+def test_two_process_nccl_matches_single_gpu(p2p):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "sharded_check.py"), "--config", "c3",
-           "--P", "30001"]
+           "--P", "30001"] + (["--p2p"] if p2p else [])
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_CHECK_OK" in r.stdout

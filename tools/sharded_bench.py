@@ -29,15 +29,18 @@ from util import cloud_tensors, settings_from  # noqa: E402
 PHASES = ["preprocess", "all_gather", "order", "render", "all_reduce", "render_bwd", "reduce_scatter", "preprocess_bwd"]
 
 
-def sharded_step(plan, ex, rs, loc, dL, ev=None):
+def sharded_step(plan, ex, rs, loc, dL, ev=None, peer=None):
     """One forward+backward through the step functions (what _ShardedRasterize does), with optional phase events."""
     mark = (lambda: ev.append(torch.cuda.Event(enable_timing=True)) or ev[-1].record()) if ev is not None else (lambda: None)
     empty = torch.empty(0, device=dL.device)
     mark()
     buf = S.shard_preprocess(plan, rs, loc["means3D"], loc["shs"], empty, loc["opacities"], loc["scales"],
-                             loc["rotations"], empty)
+                             loc["rotations"], empty, peer=peer)
     mark()
-    ex.all_gather_inplace(S.exchange_view(buf))
+    if peer is not None:
+        ex.barrier(dL.device)
+    else:
+        ex.all_gather_inplace(S.exchange_view(buf))
     mark()
     S.shard_order(buf)
     mark()
@@ -63,12 +66,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--single", action="store_true")
+    ap.add_argument("--p2p", action="store_true", help="fused preprocess + all-gather over peer memory")
     ap.add_argument("--sync-each", action="store_true", help="host-synchronise after every timed step (diagnostic)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device("cuda", local)
     S.init_distributed("nccl", dev)
-    cloud, cams = synth.make_config(a.config, P=a.P)
+    cloud, cams = synth.make_config_cached(a.config, P=a.P)
     P = cloud.means3D.shape[0]
     H, W = cams[0].image_height, cams[0].image_width
     bg = (0.0, 0.0, 0.0)
@@ -82,15 +86,18 @@ def main():
         del full
     torch.cuda.empty_cache()
 
+    from gaussianeditor_b200.rasterizer import _geometry_bytes
+    from gaussianeditor_b200 import _lib
+    peer = S.PeerWorkspace(_geometry_bytes(_lib.load(), plan.P_pad), ex, dev) if a.p2p else None
     for i in range(a.warmup):
-        sharded_step(plan, ex, settings[i % len(settings)], loc, dL)
+        sharded_step(plan, ex, settings[i % len(settings)], loc, dL, peer=peer)
     torch.cuda.synchronize(); dist.barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ndev0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     t0.record()
     Rs = []
     for i in range(a.steps):
-        _, _, buf = sharded_step(plan, ex, settings[i % len(settings)], loc, dL)
+        _, _, buf = sharded_step(plan, ex, settings[i % len(settings)], loc, dL, peer=peer)
         Rs.append(buf.R)
         if a.sync_each:
             torch.cuda.synchronize()
@@ -104,7 +111,7 @@ def main():
     acc_ms = np.zeros(len(PHASES))
     for i in range(a.steps):
         ev = []
-        sharded_step(plan, ex, settings[i % len(settings)], loc, dL, ev)
+        sharded_step(plan, ex, settings[i % len(settings)], loc, dL, ev, peer=peer)
         torch.cuda.synchronize()
         acc_ms += np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(len(PHASES))])
     phase = torch.tensor(acc_ms / a.steps, device=dev)
@@ -139,7 +146,8 @@ def main():
             "metric": "forward+backward Mpixels/s, Gaussian-sharded", "value": W * H / (m * 1e-3) / 1e6, "unit": "Mpixels/s",
             "n_gpus": world, "ms_per_step": m, "scaling": "strong",
             "config": {"workload": f"{a.config}: P={P}, SH degree {cloud.sh_degree}, {W}x{H}, {len(cams)} ring cameras cycled",
-                       "parallelism": f"gaussian-shard x{world} + tile-row interleave"},
+                       "parallelism": f"gaussian-shard x{world} + tile-row interleave",
+                       "exchange": "fused peer stores (TMA) + barrier" if a.p2p else "NCCL all-gather"},
             "R_rank0_mean": float(np.mean(Rs)),
             "phase_ms_max_over_ranks": {n: round(float(v), 4) for n, v in zip(PHASES, phase_max.tolist())},
             "single_gpu_ms_per_step": single_ms, "cudaMallocs_in_timed_region": ndev1 - ndev0,
@@ -147,6 +155,9 @@ def main():
             "exchange_bytes_per_step": {"all_gather": plan.P_pad * 48, "all_reduce": 16 * W * H,
                                         "reduce_scatter": plan.P_pad * 48},
         }))
+    if peer is not None:
+        del buf
+        peer.close()
     dist.destroy_process_group()
 
 

@@ -25,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c3")
     ap.add_argument("--P", type=int, default=None)
+    ap.add_argument("--p2p", action="store_true", help="fused preprocess + all-gather over peer memory")
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
@@ -43,7 +44,7 @@ def main():
                                                 shs=full["shs"], scales=full["scales"], rotations=full["rotations"])
     (color * dL).sum().backward()
 
-    rast = S.ShardedGaussianRasterizer(rs, P)
+    rast = S.ShardedGaussianRasterizer(rs, P, p2p=a.p2p)
     plan = rast.plan
     loc = {k: S.shard_slice(v.detach(), plan).clone().requires_grad_(True) for k, v in full.items()}
     lm2 = torch.zeros_like(loc["means3D"], requires_grad=True)
@@ -52,6 +53,14 @@ def main():
     (scolor * dL).sum().backward()
     torch.cuda.synchronize()
 
+    if a.p2p:  # second round through the recycled peer workspace
+        for v in list(loc.values()) + [lm2]:
+            v.grad = None
+        del scolor, sradii, sdepth
+        scolor, sradii, sdepth = rast(means3D=loc["means3D"], means2D=lm2, opacities=loc["opacities"], shs=loc["shs"],
+                                      scales=loc["scales"], rotations=loc["rotations"])
+        (scolor * dL).sum().backward()
+        torch.cuda.synchronize()
     ok = torch.equal(scolor, color) and torch.equal(sdepth, depth) and torch.equal(sradii, S.shard_slice(radii, plan))
     worst = 0.0
     pairs = [(loc[k].grad, S.shard_slice(full[k].grad, plan)) for k in loc] + [(lm2.grad, S.shard_slice(m2.grad, plan))]
@@ -61,8 +70,11 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"world={world} P={P} R_rank0={S._ShardedRasterize.last_buffers.R} worst_grad_rel_l2={worst:.2e}")
+        print(f"world={world} p2p={a.p2p} P={P} R_rank0={S._ShardedRasterize.last_R} worst_grad_rel_l2={worst:.2e}")
         print("SHARDED_CHECK_OK" if int(flag) == 1 else "SHARDED_CHECK_FAILED")
+    if rast.pool is not None:
+        del scolor, sradii, sdepth
+        rast.pool.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag) == 1 else 1)
 
