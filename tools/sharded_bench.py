@@ -29,15 +29,15 @@ from util import cloud_tensors, settings_from  # noqa: E402
 PHASES = ["preprocess", "all_gather", "order", "render", "all_reduce", "render_bwd", "reduce_scatter", "preprocess_bwd"]
 
 
-def sharded_step(plan, ex, rs, loc, dL, ev=None, peer=None):
+def sharded_step(plan, ex, rs, loc, dL, ev=None, ws=None):
     """One forward+backward through the step functions (what _ShardedRasterize does), with optional phase events."""
     mark = (lambda: ev.append(torch.cuda.Event(enable_timing=True)) or ev[-1].record()) if ev is not None else (lambda: None)
     empty = torch.empty(0, device=dL.device)
     mark()
     buf = S.shard_preprocess(plan, rs, loc["means3D"], loc["shs"], empty, loc["opacities"], loc["scales"],
-                             loc["rotations"], empty, peer=peer)
+                             loc["rotations"], empty, ws=ws)
     mark()
-    if peer is not None:
+    if buf.peer is not None:
         ex.barrier(dL.device)
     else:
         ex.all_gather_inplace(S.exchange_view(buf))
@@ -51,7 +51,7 @@ def sharded_step(plan, ex, rs, loc, dL, ev=None, peer=None):
     mark()
     acc = S.shard_backward_render(buf, dL)   # loss = (color * dL).sum()  ->  dL/dcolor = dL
     mark()
-    acc_slice = torch.empty(plan.slice_len, S.ACC_STRIDE, dtype=torch.float32, device=dL.device)
+    acc_slice = buf.alloc("acc_slice", plan.slice_len * S.ACC_STRIDE, torch.float32, dL.device).view(plan.slice_len, S.ACC_STRIDE)
     ex.reduce_scatter_sum(acc, acc_slice)
     mark()
     grads = S.shard_backward_preprocess(buf, acc_slice)
@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--single", action="store_true")
     ap.add_argument("--p2p", action="store_true", help="fused preprocess + all-gather over peer memory")
+    ap.add_argument("--no-pool", action="store_true", help="allocate every scratch buffer per step (diagnostic)")
     ap.add_argument("--sync-each", action="store_true", help="host-synchronise after every timed step (diagnostic)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -88,16 +89,17 @@ def main():
 
     from gaussianeditor_b200.rasterizer import _geometry_bytes
     from gaussianeditor_b200 import _lib
-    peer = S.PeerWorkspace(_geometry_bytes(_lib.load(), plan.P_pad), ex, dev) if a.p2p else None
+    pool = S.WorkspacePool(ex, _geometry_bytes(_lib.load(), plan.P_pad), a.p2p) if not a.no_pool else None
+    ws = pool.take(dev) if pool is not None else None   # one step in flight at a time: one workspace
     for i in range(a.warmup):
-        sharded_step(plan, ex, settings[i % len(settings)], loc, dL, peer=peer)
+        sharded_step(plan, ex, settings[i % len(settings)], loc, dL, ws=ws)
     torch.cuda.synchronize(); dist.barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ndev0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     t0.record()
     Rs = []
     for i in range(a.steps):
-        _, _, buf = sharded_step(plan, ex, settings[i % len(settings)], loc, dL, peer=peer)
+        _, _, buf = sharded_step(plan, ex, settings[i % len(settings)], loc, dL, ws=ws)
         Rs.append(buf.R)
         if a.sync_each:
             torch.cuda.synchronize()
@@ -111,7 +113,7 @@ def main():
     acc_ms = np.zeros(len(PHASES))
     for i in range(a.steps):
         ev = []
-        sharded_step(plan, ex, settings[i % len(settings)], loc, dL, ev, peer=peer)
+        sharded_step(plan, ex, settings[i % len(settings)], loc, dL, ev, ws=ws)
         torch.cuda.synchronize()
         acc_ms += np.array([ev[k].elapsed_time(ev[k + 1]) for k in range(len(PHASES))])
     phase = torch.tensor(acc_ms / a.steps, device=dev)
@@ -155,9 +157,9 @@ def main():
             "exchange_bytes_per_step": {"all_gather": plan.P_pad * 48, "all_reduce": 16 * W * H,
                                         "reduce_scatter": plan.P_pad * 48},
         }))
-    if peer is not None:
+    if pool is not None:
         del buf
-        peer.close()
+        pool.close()
     dist.destroy_process_group()
 
 
