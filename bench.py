@@ -14,7 +14,9 @@ protocol).  The 8 ring cameras of the config are cycled step by step.
            L2, so no separate L2 flush is needed between iterations.
   e2e    : the same step through the public API with HOST buffers: each step copies the camera and the G image
            from pinned host memory (H2D; the 23 MB image on a side stream, overlapping the forward) and reads the
-           loss back (D2H) inside the timed region.
+           loss back (D2H into pinned memory) inside the timed region. The read-back is asynchronous and the host
+           consumes each step's loss while the NEXT step is already enqueued (what a training loop that logs its
+           loss does); all K losses are on the host before the closing event is recorded. Both arms do the same.
   N > 1  : one process per GPU (torchrun), the cloud replicated, every rank renders its own camera stream --
            the path shards over views with no data-path collective ("weak" scaling); value = all ranks' pixels
            / max-over-ranks time.
@@ -145,6 +147,28 @@ class Workload:
     def join_host_inputs(self):
         torch.cuda.current_stream(self.dev).wait_stream(self.copy_stream)
 
+    def read_back(self, loss):
+        """e2e leg: D2H of the step's result into pinned memory, asynchronously; returns a handle whose wait() gives
+        the float once the copy has landed."""
+        if not hasattr(self, "_loss_host"):
+            self._loss_host = [torch.zeros(1).pin_memory() for _ in range(2)]
+            self._loss_slot = 0
+        buf = self._loss_host[self._loss_slot]
+        self._loss_slot ^= 1
+        buf.copy_(loss.detach().reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        return PendingLoss(buf, ev)
+
+
+class PendingLoss:
+    def __init__(self, buf, ev):
+        self.buf, self.ev = buf, ev
+
+    def wait(self) -> float:
+        self.ev.synchronize()
+        return float(self.buf[0])
+
 
 # ---------------------------------------------------------------------------------------------------------
 # ours: through the public drop-in API
@@ -183,7 +207,7 @@ class OursRunner:
         loss = (color * G).sum()
         loss.backward()
         if host:
-            return float(loss.item())
+            return wl.read_back(loss)
         return loss
 
     def describe(self):
@@ -229,7 +253,7 @@ class ReferenceCudaRunner:
         self.g = self.R.backward(dL_dcolor=G, radii=radii, R=R, **common)
         self.last = (radii, R)
         if host:
-            return float(loss.item())
+            return wl.read_back(loss)
         return loss
 
     def describe(self):
@@ -342,8 +366,16 @@ def main():
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        pending, losses = None, []
         for i in range(n):
-            runner.step(i + rank * 3, host=host)
+            cur = runner.step(i + rank * 3, host=host)
+            if host:  # consume step i-1's loss on the host while step i runs on the GPU
+                if pending is not None:
+                    losses.append(pending.wait())
+                pending = cur
+        if pending is not None:
+            losses.append(pending.wait())
+            assert len(losses) == n and all(np.isfinite(losses))
         b.record()
         barrier()
         ms = a.elapsed_time(b)
@@ -362,7 +394,7 @@ def main():
     clocks = sampler.stop()
     launches = (_lib.launch_count() - launches0) if args.impl == "ours" else None
     for i in range(3):
-        runner.step(i, host=True)
+        runner.step(i, host=True).wait()
     ms_e2e = timed(args.steps, host=True)
     desc = runner.describe()
 
@@ -393,17 +425,25 @@ def main():
         dom = max(stages, key=stages.get)
         peak, peak_src = measured_peaks()
         ach = ab[dom] / (stages[dom] * 1e-3) / 1e9
-        traffic = None
-        try:  # DRAM bytes per launch from the committed ncu --set full capture of the same command
+        traffic, issue = None, None
+        try:  # DRAM bytes and instruction count per launch from the committed ncu --set full capture of the same command
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                traffic = json.load(f)["kernels"][dom]["dram_bytes"]
+                kd = json.load(f)["kernels"][dom]
+            traffic = kd["dram_bytes"]
+            # second lens for the issue-bound render kernels: warp instructions per launch (ncu) / live kernel time,
+            # against 148 SMs x 4 schedulers x 1 instruction per clock at the clock sampled during the timed region
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_inst = 148 * 4 * sm_mhz * 1e6
+            issue = {"warp_inst_per_launch": kd["warp_inst"], "achieved_Ginst_s": kd["warp_inst"] / (stages[dom] * 1e-3) / 1e9,
+                     "peak_Ginst_s": peak_inst / 1e9, "frac": kd["warp_inst"] / (stages[dom] * 1e-3) / peak_inst,
+                     "ipc_per_sm_under_ncu": kd.get("ipc_per_sm")}
         except Exception:
             pass
         line["roofline"] = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                             "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                             "note": "the render kernels are FP32-issue bound, not HBM bound (DESIGN.md section 5): "
                                     "frac is the share of the HBM time the algorithmic bytes would need",
-                            "alg_bytes": ab[dom], "kernel_ms": stages[dom],
+                            "alg_bytes": ab[dom], "kernel_ms": stages[dom], "issue": issue,
                             "all": {k: {"ms": round(stages[k], 4), "alg_GB": round(ab[k] / 1e9, 4),
                                         "GBps": round(ab[k] / (stages[k] * 1e-3) / 1e9, 1),
                                         "frac": round(ab[k] / (stages[k] * 1e-3) / 1e9 / peak, 4)}

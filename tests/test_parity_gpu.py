@@ -47,7 +47,7 @@ def _small_cases():
             ("c3odd", c3, cam_odd, (0.2, 0.5, 0.7))]
 
 
-@pytest.mark.parametrize("fwd_variant", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("fwd_variant", [0, 1, 2, 3, 4, 5])
 def test_forward_matches_reference_cuda_bit_exact(fwd_variant):
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
@@ -379,3 +379,76 @@ def test_hd_frame_partial_tile_row_and_debug_flag():
     assert torch.equal(radii, ref["radii"]) and torch.equal(v["ranges"], ref["state"]["ranges"])
     assert torch.equal(color, ref["color"]) and torch.equal(depth, ref["depth"])
     assert torch.equal(v["n_contrib"], ref["state"]["n_contrib"])
+
+
+def _check_forward_bit_exact(ours, ref, name):
+    v, s = ours["views"], ref["state"]
+    assert ours["R"] == ref["R"], name
+    assert torch.equal(ours["radii"], ref["radii"]), name
+    assert torch.equal(ours["color"], ref["color"]) and torch.equal(ours["depth"], ref["depth"]), name
+    assert torch.equal(v["n_contrib"].flatten(), s["n_contrib"].flatten().to(torch.int32)), name
+    assert torch.equal(v["final_T"].flatten(), s["final_T"].flatten()), name
+    assert torch.equal(v["point_list"], s["point_list"].to(torch.int32)), name
+
+
+@pytest.mark.parametrize("cfg", ["c2", "c3"])
+def test_full_size_configs_match_reference_cuda(cfg):
+    """BASELINE configs 2 (100k, SH 0, 800x800) and 3 (1M, SH 3, 1600x1200) at FULL size against the reference's
+    own CUDA build: forward bit-exact (images, radii, n_contrib, final_T, the complete sorted list).
+
+    Gradients are judged against the fp64 CPU oracle (ground truth), because at full size the REFERENCE is the
+    inaccurate one: its ~10^6 per-pixel fp32 atomics on the largest splats swamp small addends and under-count
+    (config 3: reference 2.5e-4 .. 6.3e-4 relative L2 from fp64; this repo 1e-6 .. 1.3e-5, like the fp32 CPU oracle).
+    So: ours vs fp64 <= 5e-5, and ours vs reference no further apart than the reference is from the truth."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    cloud, cams = synth.make_config(cfg)
+    cam = cams[-1]
+    bg = (0.1, 0.2, 0.3)
+    dL = np.random.default_rng(11).uniform(size=(3, cam.image_height, cam.image_width)).astype(np.float32)
+    ours = run_ours(cloud, cam, bg, dL=dL)
+    ref = _ref_run(cloud, cam, bg, dL=dL)
+    ref2 = _ref_run(cloud, cam, bg, dL=dL)
+    _check_forward_bit_exact(ours, ref, cfg)
+    f64 = cpu_oracle.forward_from(cloud, cam, bg, f32=False)
+    truth = f64.backward(dL)
+    f64.close()
+    for a, b in [("dmean3D", "dL_dmeans3D"), ("dmean2D", "dL_dmeans2D"), ("dopacity", "dL_dopacity"),
+                 ("dscale", "dL_dscales"), ("drot", "dL_drotations"), ("dsh", "dL_dsh")]:
+        g, r, t = ours["grads"][a].cpu().numpy(), ref["grads"][b].cpu().numpy(), truth[a]
+        noise = rel_l2(ref2["grads"][b].cpu().numpy(), r)
+        ours_err, ref_err = rel_l2(g, t), rel_l2(r, t)
+        assert ours_err <= 5e-5, (cfg, a, ours_err)
+        assert rel_l2(g, r) <= 1e-4 + 10 * noise + 1.5 * ref_err, (cfg, a, rel_l2(g, r), noise, ref_err)
+
+
+def test_full_size_properties_config4():
+    """BASELINE config 4 (5M Gaussians, 1920x1080) on one GPU: list invariants, determinism of the forward
+    (bit-identical across two runs), finite gradients that vanish exactly for culled Gaussians."""
+    cloud, cams = synth.make_config("c4")
+    cam = cams[3]
+    dL = np.random.default_rng(2).uniform(size=(3, cam.image_height, cam.image_width)).astype(np.float32)
+    out = run_ours(cloud, cam, (0, 0, 0), dL=dL)
+    v, R = out["views"], out["R"]
+    assert R == int(v["tiles_touched"].to(torch.int64).sum())
+    ranges = v["ranges"].to(torch.int64)
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert int(lens.sum()) == R and int(lens.min()) >= 0 and int(ranges[:, 1].max()) == R
+    keys = v["tile_keys"]
+    keys = (keys.to(torch.int32) & 0xFFFF) if keys.dtype == torch.int16 else keys
+    assert bool((keys[1:] >= keys[:-1]).all())
+    pl = v["point_list"].to(torch.int64)
+    d = v["records"][:, 6][pl]
+    same = keys[1:] == keys[:-1]
+    assert bool((d[1:][same] >= d[:-1][same]).all())
+    tie = same & (d[1:] == d[:-1])
+    assert bool((pl[1:][tie] > pl[:-1][tie]).all())
+    assert float(v["final_T"].min()) >= float(np.float32(1e-4)) and float(v["final_T"].max()) <= 1.0
+    vis = out["radii"] > 0
+    for k, g in out["grads"].items():
+        if g is not None:
+            assert torch.isfinite(g).all(), k
+            assert float(g[~vis].abs().sum()) == 0.0, k
+    again = run_ours(cloud, cam, (0, 0, 0))
+    assert torch.equal(again["color"], out["color"]) and torch.equal(again["radii"], out["radii"])
+    assert torch.equal(again["views"]["point_list"], v["point_list"]) and again["R"] == R
