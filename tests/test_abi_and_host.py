@@ -123,3 +123,26 @@ def test_synthetic_configs_are_deterministic():
     centre = -W2C[:3, :3].T @ W2C[:3, 3]
     assert np.allclose(centre, cam.campos, atol=1e-5)
     assert abs(cam.tanfovx / cam.tanfovy - 1600 / 1200) < 1e-6
+
+
+def test_shard_entry_points_validate_before_touching_the_device():
+    """Gaussian-sharded C-ABI (gsr_shard_*): ownership and slice arguments are checked up front."""
+    lib = _lib.load()
+    dummy = C.c_void_p(256)
+    host = (C.c_int32 * 1)()
+    s = _lib.Settings(64, 64, 1.0, 1.0, 1.0, 0, 1, 0, 0, dummy, dummy, dummy, dummy)
+    for stride, phase in [(0, 0), (2, 2), (3, -1)]:
+        own = _lib.TileOwner(stride, phase)
+        rc = lib.gsr_shard_order(C.byref(s), C.byref(own), 100, dummy, 1 << 20, dummy, host, None)
+        assert rc == -1 and b"row_stride" in lib.gsr_last_error()
+    shard = _lib.Cloud(10, dummy, dummy, dummy, None, dummy, dummy, None)
+    # slice [95, 95+10) does not fit P_total = 100; slice shorter than the shard
+    assert lib.gsr_shard_preprocess(C.byref(s), C.byref(shard), 100, 95, 10, dummy, 1 << 20, dummy, None) == -1
+    assert b"does not fit" in lib.gsr_last_error()
+    assert lib.gsr_shard_preprocess(C.byref(s), C.byref(shard), 100, 0, 5, dummy, 1 << 20, dummy, None) == -1
+    peers = (C.c_void_p * 9)(*([256] * 9))
+    assert lib.gsr_shard_preprocess_p2p(C.byref(s), C.byref(shard), 100, 0, 10, peers, 9, 0, 1 << 20, dummy, None) == -1
+    assert b"world" in lib.gsr_last_error()
+    assert lib.gsr_shard_preprocess_p2p(C.byref(s), C.byref(shard), 100, 0, 10, peers, 2, 2, 1 << 20, dummy, None) == -1
+    ev = _lib.ExchangeView()
+    assert lib.gsr_view_exchange(dummy, -1, C.byref(ev)) == -1
