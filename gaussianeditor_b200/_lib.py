@@ -24,6 +24,7 @@ SYMBOLS = [
     "gsr_view_exchange", "gsr_shard_preprocess", "gsr_shard_order", "gsr_shard_render", "gsr_shard_backward_render",
     "gsr_shard_backward_preprocess",
     "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close", "gsr_peer_free", "gsr_shard_preprocess_p2p",
+    "gsr_forward_preprocess_raw", "gsr_backward_raw",
 ]
 
 
@@ -63,6 +64,17 @@ class BinningView(C.Structure):
 
 class ImageView(C.Structure):
     _fields_ = [("final_T", C.c_void_p), ("n_contrib", C.c_void_p), ("ranges", C.c_void_p)]
+
+
+class RawCloud(C.Structure):
+    _fields_ = [("P", C.c_int32), ("means3D", C.c_void_p), ("opacity_logits", C.c_void_p), ("features_dc", C.c_void_p),
+                ("features_rest", C.c_void_p), ("log_scales", C.c_void_p), ("raw_rotations", C.c_void_p)]
+
+
+class RawGrads(C.Structure):
+    _fields_ = [("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p), ("dL_dopacity_logits", C.c_void_p),
+                ("dL_dfeatures_dc", C.c_void_p), ("dL_dfeatures_rest", C.c_void_p), ("dL_dlog_scales", C.c_void_p),
+                ("dL_draw_rotations", C.c_void_p)]
 
 
 class TileOwner(C.Structure):
@@ -147,6 +159,11 @@ def load():
     lib.gsr_peer_free.restype = C.c_int; lib.gsr_peer_free.argtypes = [vp]
     lib.gsr_shard_preprocess_p2p.restype = C.c_int
     lib.gsr_shard_preprocess_p2p.argtypes = [S, Cl, i32, i32, i32, C.POINTER(vp), i32, i32, sz, vp, vp]
+    lib.gsr_forward_preprocess_raw.restype = C.c_int
+    lib.gsr_forward_preprocess_raw.argtypes = [S, C.POINTER(RawCloud), vp, sz, vp, vp, vp]
+    lib.gsr_backward_raw.restype = C.c_int
+    lib.gsr_backward_raw.argtypes = [S, C.POINTER(RawCloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz,
+                                     C.POINTER(RawGrads), vp]
     if lib.gsr_abi_version() != 2:
         raise RuntimeError("libgsr_b200.so ABI version mismatch")
     _lib = lib

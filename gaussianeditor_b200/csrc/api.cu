@@ -233,6 +233,82 @@ int gsr_apply_weights(const gsr_settings* s, const gsr_cloud* c, int32_t R, void
   return launch_apply_weights(*s, g, b, im, image_weights, CH, weights, cnt, st);
 }
 
+// ---- fused activations (raw parameters) --------------------------------------------------------------------
+static int raw_to_cloud(const gsr_settings* s, const gsr_raw_cloud* r, gsr_cloud& c) {
+  if (!s || !r) { set_error("null settings/cloud"); return GSR_ERR_INVALID; }
+  c = gsr_cloud{};
+  c.P = r->P; c.means3D = r->means3D; c.opacities = r->opacity_logits; c.shs = r->features_dc;
+  c.scales = r->log_scales; c.rotations = r->raw_rotations;
+  int rc = validate(s, &c);
+  if (rc) return rc;
+  if (r->P > 0 && s->sh_coeffs > 1 && !r->features_rest) { set_error("features_rest is null but sh_coeffs = %d", s->sh_coeffs); return GSR_ERR_INVALID; }
+  if (r->features_rest && (reinterpret_cast<uintptr_t>(r->features_rest) & 15)) { set_error("features_rest must be 16-byte aligned"); return GSR_ERR_INVALID; }
+  return GSR_OK;
+}
+
+int gsr_forward_preprocess_raw(const gsr_settings* s, const gsr_raw_cloud* r, void* geometry, size_t geometry_bytes,
+                               int32_t* radii, int32_t* num_rendered_host, void* stream) {
+  gsr_cloud c;
+  int rc = raw_to_cloud(s, r, c);
+  if (rc) return rc;
+  if (!num_rendered_host) { set_error("num_rendered_host is null"); return GSR_ERR_INVALID; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c.P == 0) { *num_rendered_host = 0; return GSR_OK; }
+  if (!radii || !geometry) { set_error("radii / geometry workspace is null"); return GSR_ERR_INVALID; }
+  GeometryWS g;
+  if (!carve_geometry(geometry, c.P, g)) return GSR_ERR_CUDA;
+  if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
+  {
+    StageScope t(ST_PRE_FWD, st);
+    rc = launch_preprocess_fwd(*s, c, g, radii, st, nullptr, 0, true, r->features_rest);
+  }
+  if (rc) return rc;
+  StageScope t(ST_DEPTH_SCAN, st);
+  return run_depth_order_and_scan(c, g, num_rendered_host, st, s->debug != 0);
+}
+
+int gsr_backward_raw(const gsr_settings* s, const gsr_raw_cloud* r, int32_t R, const void* geometry,
+                     size_t geometry_bytes, const void* binning, size_t binning_bytes, const void* image,
+                     size_t image_bytes, const int32_t* radii, const float* dL_dout_color, void* scratch,
+                     size_t scratch_bytes, const gsr_raw_grads* gr, void* stream) {
+  gsr_cloud c;
+  int rc = raw_to_cloud(s, r, c);
+  if (rc) return rc;
+  if (!gr || !dL_dout_color) { set_error("grads / dL_dout_color is null"); return GSR_ERR_INVALID; }
+  if (c.P == 0) return GSR_OK;
+  if (!gr->dL_dmeans3D || !gr->dL_dmeans2D || !gr->dL_dopacity_logits || !gr->dL_dfeatures_dc || !gr->dL_dlog_scales ||
+      !gr->dL_draw_rotations || (s->sh_coeffs > 1 && !gr->dL_dfeatures_rest)) {
+    set_error("a gradient output pointer is null");
+    return GSR_ERR_INVALID;
+  }
+  if ((reinterpret_cast<uintptr_t>(gr->dL_draw_rotations) & 15) || (reinterpret_cast<uintptr_t>(gr->dL_dfeatures_rest) & 15)) {
+    set_error("dL_draw_rotations / dL_dfeatures_rest must be 16-byte aligned");
+    return GSR_ERR_INVALID;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  GeometryWS g; BinningWS b; ImageWS im;
+  rc = carve_all(s, &c, R, const_cast<void*>(geometry), geometry_bytes, const_cast<void*>(binning), binning_bytes,
+                 const_cast<void*>(image), image_bytes, g, b, im);
+  if (rc) return rc;
+  const size_t need = gsr_backward_scratch_bytes(c.P);
+  if (!scratch || scratch_bytes < need) { set_error("backward scratch too small: %zu < %zu", scratch_bytes, need); return GSR_ERR_WORKSPACE; }
+  {
+    StageScope t(ST_RENDER_BWD, st);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)c.P * ACC_STRIDE * sizeof(float), st);
+    if (e != cudaSuccess) return check_cuda(e, "scratch memset");
+    if (R > 0) {
+      rc = launch_render_bwd(*s, g, b, im, dL_dout_color, (float*)scratch, st);
+      if (rc) return rc;
+    }
+  }
+  gsr_grads full{};
+  full.dL_dmeans3D = gr->dL_dmeans3D; full.dL_dmeans2D = gr->dL_dmeans2D; full.dL_dopacity = gr->dL_dopacity_logits;
+  full.dL_dsh = gr->dL_dfeatures_dc; full.dL_dscales = gr->dL_dlog_scales; full.dL_drotations = gr->dL_draw_rotations;
+  RawBackward raw{r->features_rest, gr->dL_dfeatures_rest};
+  StageScope t(ST_PRE_BWD, st);
+  return launch_preprocess_bwd(*s, c, g, radii, (const float*)scratch, full, st, &raw);
+}
+
 // ---- Gaussian-sharded multi-GPU path ---------------------------------------------------------------------
 static int check_owner(const gsr_tile_owner* o, TileOwner& own) {
   if (!o || o->row_stride < 1 || o->row_phase < 0 || o->row_phase >= o->row_stride) {

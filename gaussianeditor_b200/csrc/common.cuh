@@ -97,8 +97,11 @@ int check_launch(const char* what, bool debug, cudaStream_t st);
 
 // ---- stage entry points (host side; each file owns its kernels) ------------------------------------------
 // peer_records/npeers: fused all-gather of the sharded path (every rank's view of this shard's record slice), else 0
+// raw selects the RAW variant (fused activations): c.opacities / c.scales / c.rotations are then the raw parameters,
+// c.shs is features_dc [P,1,3] and features_rest [P,M-1,3] holds the other coefficients (may be null when M == 1).
 int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
-                          cudaStream_t st, SplatRecord* const* peer_records = nullptr, int npeers = 0);
+                          cudaStream_t st, SplatRecord* const* peer_records = nullptr, int npeers = 0, bool raw = false,
+                          const float* features_rest = nullptr);
 int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
                              bool debug);
 // Sharded path: recompute tiles_touched (owned tile rows only) and the sort identity for all P gathered Gaussians.
@@ -111,8 +114,13 @@ int launch_render_fwd(const gsr_settings& s, const GeometryWS& g, const BinningW
                       float* out_color, float* out_depth, cudaStream_t st, const TileOwner& own = TileOwner());
 int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
                       const float* dL_dpix, float* acc, cudaStream_t st, const TileOwner& own = TileOwner());
+// raw != nullptr: RAW variant -- gradients w.r.t. the raw parameters (gr.dL_dsh = d features_dc, raw->dL_dfeatures_rest)
+struct RawBackward {
+  const float* features_rest;
+  float* dL_dfeatures_rest;
+};
 int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
-                          const float* acc, const gsr_grads& gr, cudaStream_t st);
+                          const float* acc, const gsr_grads& gr, cudaStream_t st, const RawBackward* raw = nullptr);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
 int launch_apply_weights(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
                          const float* image_weights, int CH, float* weights, int32_t* cnt, cudaStream_t st);

@@ -66,6 +66,11 @@ struct PbArgs {
   float* dL_dsh;
   float* dL_dscales;
   float* dL_drotations;
+  // RAW variant (fused activations): shs = features_dc [P,1,3], dL_dsh = d features_dc, opacities = logits,
+  // scales = log-scales, rotations = unnormalised; gradients are taken w.r.t. those raw parameters
+  const float* opacities;
+  const float* features_rest;
+  float* dL_dfeatures_rest;
 };
 
 __device__ __forceinline__ M3 quat_to_R(float r, float x, float y, float z) {
@@ -76,9 +81,12 @@ __device__ __forceinline__ M3 quat_to_R(float r, float x, float y, float z) {
   return R;
 }
 
-template <bool BULK>
+template <bool BULK, bool RAW = false>
 __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs a) {
+  static_assert(!(BULK && RAW), "the RAW variant stages its SH block itself");
   __shared__ __align__(16) float rows[BULK ? PB_THREADS * ROW_WORDS : 4];
+  // RAW: the CTA's features_rest rows in (one bulk load), overwritten in place by their gradients, out (one bulk store)
+  __shared__ __align__(128) float s_rest[RAW ? PB_THREADS * 45 : 1];
   __shared__ uint64_t bar;
   const int idx = blockIdx.x * PB_THREADS + threadIdx.x;
   const bool live = idx < a.P;
@@ -86,6 +94,22 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
   const bool has_sh = a.shs != nullptr;
   float* row = BULK ? &rows[threadIdx.x * ROW_WORDS] : nullptr;
   const int nb = (a.D + 1) * (a.D + 1);  // active coefficients
+  const int K3 = RAW ? (a.M - 1) * 3 : 0;
+  bool rest_block = false, rest_loaded = false;
+  if (RAW) {
+    const int first = blockIdx.x * PB_THREADS;
+    const uint32_t bytes = (uint32_t)(min(PB_THREADS, a.P - first) * K3 * 4);
+    rest_block = bytes != 0 && (bytes & 15u) == 0;          // else: partial last block, plain loads / stores
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    rest_loaded = __syncthreads_or(vis) && rest_block && a.D > 0;
+    if (rest_loaded && threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&bar, bytes);
+      bulk_g2s(s_rest, a.features_rest + (size_t)first * K3, bytes, &bar);
+    }
+  }
 
   if (BULK) {
     if (threadIdx.x == 0) {
@@ -106,6 +130,9 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
   float dscale[3] = {0.f, 0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
   float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0, acc2 = acc0;
   float3 mean = make_float3(0.f, 0.f, 0.f);
+  float3 act_scale = make_float3(0.f, 0.f, 0.f);
+  float4 qn = make_float4(0.f, 0.f, 0.f, 0.f);
+  float raw_norm = 1.0f;
 
   if (vis) {
     const float4* ap = reinterpret_cast<const float4*>(a.acc + (size_t)idx * ACC_STRIDE);
@@ -123,9 +150,14 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
 #pragma unroll
       for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[(size_t)idx * 6 + k];
     } else {
-      sc = make_float3(a.scale_modifier * a.scales[3 * idx], a.scale_modifier * a.scales[3 * idx + 1],
-                       a.scale_modifier * a.scales[3 * idx + 2]);
+      act_scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
       q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+      if (RAW) {  // same activations as the RAW forward (preprocess_fwd.cu)
+        act_scale = make_float3(expf(act_scale.x), expf(act_scale.y), expf(act_scale.z));
+        raw_norm = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+        q = make_float4(__fdiv_rn(q.x, raw_norm), __fdiv_rn(q.y, raw_norm), __fdiv_rn(q.z, raw_norm), __fdiv_rn(q.w, raw_norm));
+      }
+      sc = make_float3(a.scale_modifier * act_scale.x, a.scale_modifier * act_scale.y, a.scale_modifier * act_scale.z);
       R = quat_to_R(q.x, q.y, q.z, q.w);
       // M = S * R (GLM): M[c][r] = s_r * R[c][r]
 #pragma unroll
@@ -251,6 +283,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
       drot[1] = 2 * y * (dMt.m[1][0] + dMt.m[0][1]) + 2 * z * (dMt.m[2][0] + dMt.m[0][2]) + 2 * r * (dMt.m[1][2] - dMt.m[2][1]) - 4 * x * (dMt.m[2][2] + dMt.m[1][1]);
       drot[2] = 2 * x * (dMt.m[1][0] + dMt.m[0][1]) + 2 * r * (dMt.m[2][0] - dMt.m[0][2]) + 2 * z * (dMt.m[1][2] + dMt.m[2][1]) - 4 * y * (dMt.m[2][2] + dMt.m[0][0]);
       drot[3] = 2 * r * (dMt.m[0][1] - dMt.m[1][0]) + 2 * x * (dMt.m[2][0] + dMt.m[0][2]) + 2 * y * (dMt.m[1][2] + dMt.m[2][1]) - 4 * z * (dMt.m[1][1] + dMt.m[0][0]);
+      qn = q;
     }
   }
 
@@ -259,6 +292,7 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
   // view-direction gradient, overwrite it IN PLACE with dL/dsh[k] = basis_k * dL/dRGB. Only one 12-float chunk is live
   // at a time (the first version kept all 48 + 48 values in registers: 113 regs, 16 warps/SM).
   if (BULK) mbar_wait(&bar, 0);
+  if (RAW && rest_loaded) mbar_wait(&bar, 0);
   if (has_sh && live) {
     const float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
     const float C2_0 = 1.0925484305920792f, C2_1 = -1.0925484305920792f, C2_2 = 0.31539156525252005f,
@@ -281,8 +315,11 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
     }
     const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
     float ddir[3] = {0.f, 0.f, 0.f};
-    const float* gsrc = a.shs + (size_t)idx * a.M * 3;
-    float* gdst = a.dL_dsh + (size_t)idx * a.M * 3;
+    const float* gsrc = a.shs + (size_t)idx * (RAW ? 3 : a.M * 3);     // RAW: features_dc row
+    float* gdst = a.dL_dsh + (size_t)idx * (RAW ? 3 : a.M * 3);
+    const float* rest_g = RAW ? a.features_rest + (size_t)idx * K3 : nullptr;
+    float* drest_g = RAW ? a.dL_dfeatures_rest + (size_t)idx * K3 : nullptr;
+    float* rest_s = s_rest + (RAW ? threadIdx.x * K3 : 0);
     const int nw = a.M * 3;
 #pragma unroll
     for (int cchunk = 0; cchunk < 4; cchunk++) {
@@ -295,6 +332,14 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
           float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (need) t4 = *reinterpret_cast<const float4*>(row + 12 * cchunk + 4 * q);
           v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+        }
+      } else if (RAW) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+          const int e = 12 * cchunk + i;  // element of the virtual [M,3] row: 0..2 = features_dc, the rest features_rest
+          float t = 0.f;
+          if (need && e < nb * 3) t = e < 3 ? gsrc[e] : (rest_loaded ? rest_s[e - 3] : rest_g[e - 3]);
+          v[i] = t;
         }
       } else {
 #pragma unroll
@@ -340,6 +385,13 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
 #pragma unroll
         for (int q = 0; q < 3; q++)
           *reinterpret_cast<float4*>(row + 12 * cchunk + 4 * q) = make_float4(o12[4 * q], o12[4 * q + 1], o12[4 * q + 2], o12[4 * q + 3]);
+      } else if (RAW) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+          const int e = 12 * cchunk + i;
+          if (e < 3) gdst[e] = o12[i];
+          else if (e < nw) { if (rest_block) rest_s[e - 3] = o12[i]; else drest_g[e - 3] = o12[i]; }
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 12; i++)
@@ -363,12 +415,37 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
   if (live) {
     a.dL_dmeans3D[3 * idx] = dmean[0]; a.dL_dmeans3D[3 * idx + 1] = dmean[1]; a.dL_dmeans3D[3 * idx + 2] = dmean[2];
     a.dL_dmeans2D[3 * idx] = acc0.w; a.dL_dmeans2D[3 * idx + 1] = acc1.x; a.dL_dmeans2D[3 * idx + 2] = 0.f;
-    a.dL_dcolors[3 * idx] = acc0.x; a.dL_dcolors[3 * idx + 1] = acc0.y; a.dL_dcolors[3 * idx + 2] = acc0.z;
-    a.dL_dopacity[idx] = acc2.x;
+    if (a.dL_dcolors) { a.dL_dcolors[3 * idx] = acc0.x; a.dL_dcolors[3 * idx + 1] = acc0.y; a.dL_dcolors[3 * idx + 2] = acc0.z; }
+    float dopac = acc2.x;
+    if (RAW) {
+      // chain rule through the activations: sigmoid' = o(1-o), exp' = exp, and F.normalize: (I - q q^T) / |raw|
+      if (vis) {
+        const float o = 1.0f / (1.0f + expf(-a.opacities[idx]));
+        dopac *= o * (1.0f - o);
+      }
+      dscale[0] *= act_scale.x; dscale[1] *= act_scale.y; dscale[2] *= act_scale.z;
+      const float qd = qn.x * drot[0] + qn.y * drot[1] + qn.z * drot[2] + qn.w * drot[3];
+      const float inv = 1.0f / raw_norm;
+      drot[0] = (drot[0] - qn.x * qd) * inv; drot[1] = (drot[1] - qn.y * qd) * inv;
+      drot[2] = (drot[2] - qn.z * qd) * inv; drot[3] = (drot[3] - qn.w * qd) * inv;
+    }
+    a.dL_dopacity[idx] = dopac;
+    if (a.dL_dcov3D) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) a.dL_dcov3D[(size_t)idx * 6 + k] = dcov[k];
+      for (int k = 0; k < 6; k++) a.dL_dcov3D[(size_t)idx * 6 + k] = dcov[k];
+    }
     a.dL_dscales[3 * idx] = dscale[0]; a.dL_dscales[3 * idx + 1] = dscale[1]; a.dL_dscales[3 * idx + 2] = dscale[2];
     *(reinterpret_cast<float4*>(a.dL_drotations) + idx) = make_float4(drot[0], drot[1], drot[2], drot[3]);
+  }
+  if (RAW && rest_block) {  // the block of d features_rest rows leaves with one bulk store
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int first = blockIdx.x * PB_THREADS;
+      bulk_s2g(a.dL_dfeatures_rest + (size_t)first * K3, s_rest, (uint32_t)(min(PB_THREADS, a.P - first) * K3 * 4));
+      bulk_commit();
+      bulk_wait_read0();
+    }
   }
   if (BULK) bulk_wait_read0();  // the row must stay valid until the TMA store has read it
 }
@@ -376,8 +453,11 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
 }  // namespace
 
 int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
-                          const float* acc, const gsr_grads& gr, cudaStream_t st) {
+                          const float* acc, const gsr_grads& gr, cudaStream_t st, const RawBackward* raw) {
   PbArgs a;
+  a.opacities = c.opacities;
+  a.features_rest = raw ? raw->features_rest : nullptr;
+  a.dL_dfeatures_rest = raw ? raw->dL_dfeatures_rest : nullptr;
   a.P = c.P; a.D = s.sh_degree; a.M = s.sh_coeffs; a.W = s.image_width; a.H = s.image_height;
   a.tan_fovx = s.tanfovx; a.tan_fovy = s.tanfovy;
   a.h_y = a.H / (2.0f * s.tanfovy);
@@ -393,7 +473,9 @@ int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const Geome
   const bool bulk = g_opt.preprocess_variant >= 1 && c.shs != nullptr && gr.dL_dsh != nullptr &&
                     (s.sh_coeffs * 12) % 16 == 0 && s.sh_coeffs * 12 <= 192 &&
                     (reinterpret_cast<uintptr_t>(c.shs) % 16) == 0 && (reinterpret_cast<uintptr_t>(gr.dL_dsh) % 16) == 0;
-  if (bulk)
+  if (raw)
+    preprocess_bwd_kernel<false, true><<<grid, PB_THREADS, 0, st>>>(a);
+  else if (bulk)
     preprocess_bwd_kernel<true><<<grid, PB_THREADS, 0, st>>>(a);
   else
     preprocess_bwd_kernel<false><<<grid, PB_THREADS, 0, st>>>(a);

@@ -50,6 +50,9 @@ struct PreArgs {
   uint32_t* depth_keys;
   uint32_t* ident;
   int32_t* radii;
+  // RAW kernel variant (fused activations, gsr_b200.h: gsr_raw_cloud): `opacities` are logits, `scales` log-scales,
+  // `rotations` unnormalised, `shs` is features_dc [P,1,3] and `features_rest` [P,M-1,3] holds the other coefficients.
+  const float* features_rest;
   // Fused all-gather of the Gaussian-sharded path (P2P kernel variant): the CTA's block of records is pushed with one
   // TMA bulk store per destination into the records array of every rank (own copy included) over NVLink peer memory.
   SplatRecord* peer_records[GSR_MAX_PEERS];  // pointers to THIS shard's slice inside each rank's records array
@@ -105,18 +108,26 @@ __device__ __forceinline__ float sh_channel(int deg, const float* w, ShFn sh) {
   return __fadd_rn(res, 0.5f);
 }
 
-template <bool BULK_SH, bool P2P = false>
+// torch.sigmoid / torch.exp / F.normalize restated for the RAW variant (scene/gaussian_model.py:221-258 applies them in
+// PyTorch before every render; here they cost nothing extra in HBM traffic)
+__device__ __forceinline__ float sigmoid_act(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+template <bool BULK_SH, bool P2P = false, bool RAW = false>
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreArgs a) {
+  static_assert(!(RAW && (BULK_SH || P2P)), "the RAW variant stages its SH block itself");
   __shared__ __align__(16) float sh_rows[BULK_SH ? PRE_THREADS * SH_ROW_WORDS : 4];
   __shared__ __align__(128) float4 s_rec[P2P ? PRE_THREADS * 3 : 1];  // the CTA's records, contiguous like in HBM
+  // RAW: the CTA's block of features_rest rows (128 x 12*(M-1) bytes, contiguous and 16-byte aligned in HBM although
+  // a single 180-byte row is not), fetched with ONE bulk copy
+  __shared__ __align__(128) float s_rest[RAW ? PRE_THREADS * 45 : 1];
   __shared__ uint64_t bar;
 
   const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
   const bool live = idx < a.P;
 
-  if (BULK_SH) {
+  if (BULK_SH || RAW) {
     if (threadIdx.x == 0) {
-      mbar_init(&bar, PRE_THREADS);
+      mbar_init(&bar, RAW ? 1 : PRE_THREADS);
       fence_mbar_init();
     }
     __syncthreads();
@@ -135,6 +146,18 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     vis = !(p_view.z <= 0.2f);
   }
   const bool want_sh = a.colors_precomp == nullptr;
+  const int K3 = RAW ? (a.M - 1) * 3 : 0;  // floats per features_rest row
+  bool rest_staged = false;
+  if (RAW) {
+    const int first = blockIdx.x * PRE_THREADS;
+    const uint32_t bytes = (uint32_t)(min(PRE_THREADS, a.P - first) * K3 * 4);
+    // a partial last block whose byte count is not a multiple of 16 falls back to plain loads
+    rest_staged = __syncthreads_or(vis) && a.D > 0 && bytes != 0 && (bytes & 15u) == 0;
+    if (rest_staged && threadIdx.x == 0) {
+      mbar_arrive_expect_tx(&bar, bytes);
+      bulk_g2s(s_rest, a.features_rest + (size_t)first * K3, bytes, &bar);
+    }
+  }
   if (BULK_SH) {
     // One TMA row fetch per surviving Gaussian; everybody arrives exactly once on the CTA barrier.
     const uint32_t nbytes = (uint32_t)(((a.D + 1) * (a.D + 1) * 12 + 15) & ~15);
@@ -173,8 +196,13 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
 #pragma unroll
       for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[(size_t)idx * 6 + k];
     } else {
-      const float3 scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
-      const float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+      float3 scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+      float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+      if (RAW) {
+        scale = make_float3(expf(scale.x), expf(scale.y), expf(scale.z));
+        const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);  // F.normalize eps
+        q = make_float4(__fdiv_rn(q.x, n), __fdiv_rn(q.y, n), __fdiv_rn(q.z, n), __fdiv_rn(q.w, n));
+      }
       const float sx = __fmul_rn(scale.x, a.scale_modifier), sy = __fmul_rn(scale.y, a.scale_modifier),
                   sz = __fmul_rn(scale.z, a.scale_modifier);
       const float r = q.x, x = q.y, y = q.z, z = q.w;
@@ -267,7 +295,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
         my_radius_i = max_radius;
         depth_key = __float_as_uint(p_view.z);
         rec.q0 = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-        rec.q1 = make_float4(conic.z, a.opacities[idx], p_view.z, 0.f);
+        rec.q1 = make_float4(conic.z, RAW ? sigmoid_act(a.opacities[idx]) : a.opacities[idx], p_view.z, 0.f);
       }
     }
   }
@@ -275,6 +303,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
   // ---- colour (forward.cu:20-71) ----
   uint8_t clamp_bits = 0;
   if (BULK_SH) mbar_wait(&bar, 0);  // all rows of this CTA have landed (every thread waits: no divergent exit before)
+  if (RAW && rest_staged) mbar_wait(&bar, 0);
   if (emit) {
     float3 rgb;
     if (!want_sh) {
@@ -305,6 +334,15 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
         }
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) res[ch] = sh_channel(a.D, w, [&](int k) { return v[3 * k + ch]; });
+      } else if (RAW) {
+        const float* dc = a.shs + (size_t)idx * 3;
+        const float* rest_g = a.features_rest + (size_t)idx * K3;
+        const float* rest_s = s_rest + threadIdx.x * K3;
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++)
+          res[ch] = sh_channel(a.D, w, [&](int k) {
+            return k == 0 ? dc[ch] : (rest_staged ? rest_s[3 * (k - 1) + ch] : rest_g[3 * (k - 1) + ch]);
+          });
       } else {
         const float* sh = a.shs + (size_t)idx * a.M * 3;
 #pragma unroll
@@ -362,8 +400,10 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 }  // namespace
 
 int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
-                          cudaStream_t st, SplatRecord* const* peer_records, int npeers) {
+                          cudaStream_t st, SplatRecord* const* peer_records, int npeers, bool raw,
+                          const float* features_rest) {
   PreArgs a;
+  a.features_rest = features_rest;
   a.npeers = npeers;
   for (int i = 0; i < GSR_MAX_PEERS; i++) a.peer_records[i] = i < npeers ? peer_records[i] : nullptr;
   a.P = c.P; a.D = s.sh_degree; a.M = s.sh_coeffs; a.W = s.image_width; a.H = s.image_height;
@@ -382,7 +422,9 @@ int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const Geome
   const bool bulk = g_opt.preprocess_variant >= 1 && c.colors_precomp == nullptr && c.shs != nullptr &&
                     (s.sh_coeffs * 12) % 16 == 0 && (reinterpret_cast<uintptr_t>(c.shs) % 16) == 0 &&
                     (s.sh_coeffs * 12) <= 192;
-  if (npeers > 0) {
+  if (raw) {
+    preprocess_fwd_kernel<false, false, true><<<grid, PRE_THREADS, 0, st>>>(a);
+  } else if (npeers > 0) {
     if (bulk)
       preprocess_fwd_kernel<true, true><<<grid, PRE_THREADS, 0, st>>>(a);
     else

@@ -38,9 +38,16 @@ def camera2rasterizer(viewpoint_camera, bg_color: torch.Tensor, sh_degree: int =
     return GaussianRasterizer(raster_settings=raster_settings)
 
 
-def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None):
+def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
+           fused_activations: bool = False):
     """Render the scene; background tensor must be on the GPU. Returns the reference's dictionary:
-    render [3,H,W], viewspace_points [P,3] (grad sink for densification), visibility_filter, radii, depth_3dgs."""
+    render [3,H,W], viewspace_points [P,3] (grad sink for densification), visibility_filter, radii, depth_3dgs.
+
+    ``fused_activations=True`` (opt-in, not in the reference) hands the scene model's RAW parameters
+    (``pc._opacity, pc._features_dc, pc._features_rest, pc._scaling, pc._rotation``) to the rasterizer, which applies
+    sigmoid / exp / normalize and reads the SH row from the two feature arrays inside its preprocess kernels: the
+    per-render PyTorch prologue (five elementwise kernels, a [P,16,3] ``torch.cat``) and its autograd epilogue go away.
+    Only valid for the plain SH path (no override colour, no Python-side SH / covariance)."""
     screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True,
                                           device=pc.get_xyz.device) + 0
     try:
@@ -68,6 +75,15 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
 
     means3D = pc.get_xyz
     means2D = screenspace_points
+    if fused_activations:
+        if override_color is not None or getattr(pipe, "convert_SHs_python", False) or \
+                getattr(pipe, "compute_cov3D_python", False):
+            raise ValueError("fused_activations needs the plain SH + scale/rotation path")
+        rendered_image, radii, depth = rasterizer.forward_raw(
+            means3D=means3D, means2D=means2D, opacity_logits=pc._opacity, features_dc=pc._features_dc,
+            features_rest=pc._features_rest, log_scales=pc._scaling, raw_rotations=pc._rotation)
+        return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+                "radii": radii, "depth_3dgs": depth}
     opacity = pc.get_opacity
 
     scales = rotations = cov3D_precomp = None

@@ -93,7 +93,10 @@ class _ForwardState:
     __slots__ = ("geom", "binning", "img", "radii", "num_rendered", "cap", "P", "M", "W", "H")
 
 
-def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, *, render=True):
+def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, *, render=True,
+                  raw_rest=None):
+    """Both forward halves. With ``raw_rest`` (features_rest [P,K,3]) the call is the fused-activation variant:
+    ``sh`` is features_dc [P,1,3] and opacities / scales / rotations are the raw parameters."""
     lib = _lib.load()
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:46-48
@@ -103,7 +106,12 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
     P = means3D.size(0)
     H, W = int(rs.image_height), int(rs.image_width)
     M = sh.size(1) if sh.numel() != 0 else 0
+    raw = raw_rest is not None
+    if raw:
+        M = 1 + raw_rest.size(1)
     with torch.cuda.device(device):
+        if raw:
+            raw_rest = _f32c(raw_rest, device)
         means3D = _f32c(means3D, device); opacities = _f32c(opacities, device)
         sh = _f32c(sh, device); colors_precomp = _f32c(colors_precomp, device)
         scales = _f32c(scales, device); rotations = _f32c(rotations, device)
@@ -120,8 +128,14 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         gbytes = _geometry_bytes(lib, P) if P > 0 else 0
         state.geom = torch.empty(gbytes, **u8)
         pinned = _pinned_i32(device)
-        _lib.check(lib.gsr_forward_preprocess(C.byref(s), C.byref(c), _ptr(state.geom), gbytes, _ptr(state.radii),
-                                              C.c_void_p(pinned.data_ptr()), st), "gsr_forward_preprocess")
+        if raw:
+            rc = _lib.RawCloud(P, _ptr(means3D), _ptr(opacities), _ptr(sh), _ptr(raw_rest), _ptr(scales), _ptr(rotations))
+            _lib.check(lib.gsr_forward_preprocess_raw(C.byref(s), C.byref(rc), _ptr(state.geom), gbytes,
+                                                      _ptr(state.radii), C.c_void_p(pinned.data_ptr()), st),
+                       "gsr_forward_preprocess_raw")
+        else:
+            _lib.check(lib.gsr_forward_preprocess(C.byref(s), C.byref(c), _ptr(state.geom), gbytes, _ptr(state.radii),
+                                                  C.c_void_p(pinned.data_ptr()), st), "gsr_forward_preprocess")
         ibytes = lib.gsr_image_bytes(W, H)
         state.img = torch.empty(ibytes, **u8)
         color = depth = None
@@ -162,6 +176,8 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         if P > 0:
             _r_hint[key] = max(R, int(0.9 * _r_hint.get(key, 0)))
     inputs = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
+    if raw:
+        inputs = inputs + (raw_rest,)
     return color, depth, state, inputs
 
 
@@ -220,10 +236,63 @@ class _RasterizeGaussians(torch.autograd.Function):
                 None)
 
 
+class _RasterizeGaussiansRaw(torch.autograd.Function):
+    """Fused-activation variant (gsr_forward_preprocess_raw / gsr_backward_raw): takes the scene model's
+    raw parameters, gradients come back w.r.t. them."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, opacity_logits, features_dc, features_rest, log_scales, raw_rotations,
+                raster_settings):
+        empty = torch.empty(0, dtype=torch.float32, device=means3D.device)
+        color, depth, state, inputs = _forward_impl(means3D, features_dc, empty, opacity_logits, log_scales,
+                                                    raw_rotations, empty, raster_settings, raw_rest=features_rest)
+        ctx.raster_settings = raster_settings
+        ctx.state = state
+        (m3, dc, _, op, sc, ro, _, rest) = inputs
+        ctx.save_for_backward(m3, dc, rest, op, sc, ro, state.radii, state.geom, state.binning, state.img)
+        ctx.mark_non_differentiable(state.radii)
+        _RasterizeGaussians.last_state = state
+        return color, state.radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+        lib = _lib.load()
+        rs, state = ctx.raster_settings, ctx.state
+        (means3D, dc, rest, logits, log_scales, raw_rot, radii, geom, binning, img) = ctx.saved_tensors
+        device = means3D.device
+        P, M = state.P, state.M
+        with torch.cuda.device(device):
+            grad_out_color = _f32c(grad_out_color, device)
+            f32 = dict(dtype=torch.float32, device=device)
+            d_m3 = torch.empty(P, 3, **f32); d_m2 = torch.empty(P, 3, **f32); d_op = torch.empty(P, 1, **f32)
+            d_dc = torch.empty(P, 1, 3, **f32); d_rest = torch.empty(P, M - 1, 3, **f32)
+            d_sc = torch.empty(P, 3, **f32); d_ro = torch.empty(P, 4, **f32)
+            if P > 0:
+                keep = []
+                s = _make_settings(rs, M, device, keep)
+                rc = _lib.RawCloud(P, _ptr(means3D), _ptr(logits), _ptr(dc), _ptr(rest), _ptr(log_scales), _ptr(raw_rot))
+                gr = _lib.RawGrads(_ptr(d_m3), _ptr(d_m2), _ptr(d_op), _ptr(d_dc), _ptr(d_rest), _ptr(d_sc), _ptr(d_ro))
+                sbytes = lib.gsr_backward_scratch_bytes(P)
+                scratch = torch.empty(sbytes, dtype=torch.uint8, device=device)
+                st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+                _lib.check(lib.gsr_backward_raw(C.byref(s), C.byref(rc), state.cap, _ptr(geom), geom.numel(),
+                                                _ptr(binning), binning.numel(), _ptr(img), img.numel(), _ptr(radii),
+                                                _ptr(grad_out_color), _ptr(scratch), sbytes, C.byref(gr), st),
+                           "gsr_backward_raw")
+        return d_m3, d_m2, d_op, d_dc, d_rest, d_sc, d_ro, None
+
+
 class GaussianRasterizer(nn.Module):
     def __init__(self, raster_settings):
         super().__init__()
         self.raster_settings = raster_settings
+
+    def forward_raw(self, means3D, means2D, opacity_logits, features_dc, features_rest, log_scales, raw_rotations):
+        """Opt-in fused-activation call (not part of the reference API): the arguments are the scene model's raw
+        parameters (``_xyz, _opacity, _features_dc, _features_rest, _scaling, _rotation``); sigmoid / exp / normalize
+        and the SH concatenation happen inside the preprocess kernels. Same return tuple as ``forward``."""
+        return _RasterizeGaussiansRaw.apply(means3D, means2D, opacity_logits, features_dc, features_rest, log_scales,
+                                            raw_rotations, self.raster_settings)
 
     def markVisible(self, positions):
         # __init__.py:248-256 / rasterize_points.cu:159-175

@@ -172,6 +172,41 @@ GSR_API int gsr_view_binning(const void* binning, int32_t P, int64_t num_rendere
                      int32_t image_height, gsr_binning_view* out);
 GSR_API int gsr_view_image(const void* image, int32_t image_width, int32_t image_height, gsr_image_view* out);
 
+/* ---- fused activations -----------------------------------------------------------------------
+ * Opt-in variant that takes the scene model's RAW parameters and applies the activations of
+ * scene/gaussian_model.py:221-258 inside the preprocess kernels instead of in PyTorch before every render:
+ *   opacity = sigmoid(logit), scale = exp(log_scale), rotation = raw / max(|raw|, 1e-12),
+ *   SH row  = [features_dc | features_rest]   (read from the two arrays; no torch.cat, no [P,M,3] copy).
+ * gsr_forward_preprocess_raw replaces gsr_forward_preprocess; the second forward half is the ordinary
+ * gsr_forward_render (pass a gsr_cloud with P and any non-null pointers); gsr_backward_raw replaces gsr_backward and
+ * returns gradients w.r.t. the raw parameters (chain rule through the activations included). settings.sh_coeffs is
+ * M = 1 + K, the coefficients allocated over both arrays. Results agree with the PyTorch-activated path to rounding
+ * (not bit-for-bit: torch's normalize reduces in a different order); the default entry points keep exact parity. */
+typedef struct gsr_raw_cloud {
+  int32_t P;
+  const float* means3D;        /* [P,3] */
+  const float* opacity_logits; /* [P,1] */
+  const float* features_dc;    /* [P,1,3] */
+  const float* features_rest;  /* [P,K,3], K = sh_coeffs - 1 (NULL when K == 0) */
+  const float* log_scales;     /* [P,3] */
+  const float* raw_rotations;  /* [P,4], 16-byte aligned */
+} gsr_raw_cloud;
+typedef struct gsr_raw_grads {
+  float* dL_dmeans3D;        /* [P,3] */
+  float* dL_dmeans2D;        /* [P,3] */
+  float* dL_dopacity_logits; /* [P,1] */
+  float* dL_dfeatures_dc;    /* [P,1,3] */
+  float* dL_dfeatures_rest;  /* [P,K,3] (NULL when K == 0) */
+  float* dL_dlog_scales;     /* [P,3] */
+  float* dL_draw_rotations;  /* [P,4], 16-byte aligned */
+} gsr_raw_grads;
+GSR_API int gsr_forward_preprocess_raw(const gsr_settings* s, const gsr_raw_cloud* c, void* geometry,
+                               size_t geometry_bytes, int32_t* radii, int32_t* num_rendered_host, void* stream);
+GSR_API int gsr_backward_raw(const gsr_settings* s, const gsr_raw_cloud* c, int32_t num_rendered, const void* geometry,
+                     size_t geometry_bytes, const void* binning, size_t binning_bytes, const void* image,
+                     size_t image_bytes, const int32_t* radii, const float* dL_dout_color, void* scratch,
+                     size_t scratch_bytes, const gsr_raw_grads* grads, void* stream);
+
 /* ---- Gaussian-sharded multi-GPU path (BASELINE config 4) ----------------------------------
  * The reference has no multi-GPU rasterizer; these entry points split the single-GPU pipeline at the two places
  * where the Gaussian-index decomposition (preprocess, fused preprocess backward) meets the tile decomposition

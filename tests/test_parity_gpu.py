@@ -452,3 +452,58 @@ def test_full_size_properties_config4():
     again = run_ours(cloud, cam, (0, 0, 0))
     assert torch.equal(again["color"], out["color"]) and torch.equal(again["radii"], out["radii"])
     assert torch.equal(again["views"]["point_list"], v["point_list"]) and again["R"] == R
+
+
+def _raw_params(cloud, dev, seed=0):
+    """Inverse activations of a synth.Cloud -> leaf tensors shaped like the scene model's raw parameters
+    (scene/gaussian_model.py:_xyz, _features_dc, _features_rest, _opacity, _scaling, _rotation)."""
+    g = torch.Generator().manual_seed(seed)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    op = t(cloud.opacities).clamp(1e-6, 1 - 1e-6)
+    rot = t(cloud.rotations) * (0.25 + 3.0 * torch.rand(cloud.rotations.shape[0], 1, generator=g)).to(dev)  # unnormalised
+    raw = dict(xyz=t(cloud.means3D), opacity=torch.log(op / (1 - op)), features_dc=t(cloud.shs[:, :1, :]),
+               features_rest=t(cloud.shs[:, 1:, :]), scaling=torch.log(t(cloud.scales)), rotation=rot)
+    return {k: v.contiguous().requires_grad_(True) for k, v in raw.items()}
+
+
+@pytest.mark.parametrize("deg,M,P", [(3, 16, 60013), (3, 16, 4096), (1, 4, 20000), (0, 1, 5000)])
+def test_fused_activations_match_pytorch_prologue(deg, M, P):
+    """GaussianRasterizer.forward_raw (sigmoid / exp / normalize / SH concatenation inside the
+    preprocess kernels) against the scene model's PyTorch prologue followed by the default rasterizer, forward and
+    all raw-parameter gradients. P = 60013 ends in a partial block (plain-load fallback), 4096 is all bulk copies."""
+    from gaussianeditor_b200.rasterizer import GaussianRasterizer
+    dev = torch.device("cuda")
+    cloud, cams = synth.make_config("c3", P=P)
+    cloud.shs = np.ascontiguousarray(cloud.shs[:, :M, :])
+    cloud.sh_degree = deg
+    cam = synth.ring_cameras(8, 4.5, 15.0, 640, 400, 61.0)[1]
+    rs = settings_from(cam, (0.3, 0.1, 0.2), deg, dev)
+    dL = torch.from_numpy(np.random.default_rng(5).uniform(size=(3, cam.image_height, cam.image_width)).astype(np.float32)).to(dev)
+    rast = GaussianRasterizer(rs)
+
+    a = _raw_params(cloud, dev)
+    m2a = torch.zeros_like(a["xyz"], requires_grad=True)
+    col_a, rad_a, dep_a = rast(means3D=a["xyz"], means2D=m2a, opacities=torch.sigmoid(a["opacity"]),
+                               shs=torch.cat((a["features_dc"], a["features_rest"]), dim=1),
+                               scales=torch.exp(a["scaling"]), rotations=torch.nn.functional.normalize(a["rotation"]))
+    (col_a * dL).sum().backward()
+
+    b = _raw_params(cloud, dev)
+    m2b = torch.zeros_like(b["xyz"], requires_grad=True)
+    col_b, rad_b, dep_b = rast.forward_raw(means3D=b["xyz"], means2D=m2b, opacity_logits=b["opacity"],
+                                           features_dc=b["features_dc"], features_rest=b["features_rest"],
+                                           log_scales=b["scaling"], raw_rotations=b["rotation"])
+    (col_b * dL).sum().backward()
+
+    assert float((rad_a != rad_b).float().mean()) <= 1e-4           # activations round differently in rare cases
+    ca, cb = col_a.detach().cpu().numpy(), col_b.detach().cpu().numpy()
+    assert np.mean(np.abs(ca - cb) > 1e-5 + 1e-4 * np.abs(ca)) <= 1e-4
+    assert rel_l2(dep_b.detach().cpu().numpy(), dep_a.detach().cpu().numpy()) <= 1e-5
+    same = (rad_a == rad_b)
+    for k in a:
+        ga, gb = a[k].grad, b[k].grad
+        assert gb is not None and gb.shape == ga.shape, k
+        assert torch.isfinite(gb).all(), k
+        assert rel_l2(gb[same].cpu().numpy(), ga[same].cpu().numpy()) <= 1e-4, (k, rel_l2(gb[same].cpu().numpy(), ga[same].cpu().numpy()))
+    assert rel_l2(m2b.grad[same].cpu().numpy(), m2a.grad[same].cpu().numpy()) <= 1e-4
+    assert float(b["features_rest"].grad[rad_b == 0].abs().sum()) == 0.0   # culled rows are written as exact zeros
