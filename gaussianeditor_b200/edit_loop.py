@@ -105,8 +105,9 @@ def make_view(cam: synth.Camera, device):
 
 
 def run_edit_loop(rasterizer_cls, steps=200, P=None, device="cuda", densification_interval=100, seed=0,
-                  log=None):
-    """Returns a dict with total / render wall times (CUDA-event timed) and the per-step Gaussian counts."""
+                  log=None, fused_activations=False):
+    """Returns a dict with total / render wall times (CUDA-event timed) and the per-step Gaussian counts.
+    ``fused_activations`` renders the SH pass through ``render(..., fused_activations=True)`` (B200 rasterizer only)."""
     from . import gaussian_renderer as GR
     cloud, cams = synth.make_config("c5", P=P)
     scene = EditScene(cloud, device)
@@ -135,7 +136,7 @@ def run_edit_loop(rasterizer_cls, steps=200, P=None, device="cuda", densificatio
             k = int(rng.integers(len(views)))
             e0, e1, e2, e3 = ev(), ev(), ev(), ev()
             e0.record()
-            pkg = GR.render(views[k], scene, pipe, bg)                                            # forward #1
+            pkg = GR.render(views[k], scene, pipe, bg, fused_activations=fused_activations)       # forward #1
             sem = GR.render(views[k], scene, pipe, bg,
                             override_color=scene.mask[..., None].float().repeat(1, 3))["render"]  # forward #2
             e1.record()

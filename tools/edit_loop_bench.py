@@ -9,7 +9,8 @@ from gaussianeditor_b200.rasterizer import GaussianRasterizer
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 P = int(sys.argv[2]) if len(sys.argv) > 2 else None
 out = {"config": "c5: 500k Gaussians, SH deg 3, 512x512, 48 ring cameras, guidance stubbed by a fixed noisy target, L1 loss",
-       "ours": edit_loop.run_edit_loop(GaussianRasterizer, steps=steps, P=P)}
+       "ours": edit_loop.run_edit_loop(GaussianRasterizer, steps=steps, P=P),
+       "ours_fused_activations": edit_loop.run_edit_loop(GaussianRasterizer, steps=steps, P=P, fused_activations=True)}
 try:
     from oracle import ref_cuda, ref_torch
     if ref_cuda.available():

@@ -53,6 +53,25 @@ def main():
     (scolor * dL).sum().backward()
     torch.cuda.synchronize()
 
+    # GaussianEditor's step shape: two forwards alive at once (SH render + mask render with precomputed colours), then
+    # ONE backward through the first -- exercises the workspace pool with two workspaces in flight
+    torch.manual_seed(7)
+    mask_col = torch.rand(plan.count, 3, device=dev)
+    full_col = torch.zeros(P, 3, device=dev)
+    full_col[plan.base:plan.base + plan.count] = mask_col
+    dist.all_reduce(full_col)
+    for v in list(loc.values()) + [lm2]:
+        v.grad = None
+    c1, _, _ = rast(means3D=loc["means3D"], means2D=lm2, opacities=loc["opacities"], shs=loc["shs"],
+                    scales=loc["scales"], rotations=loc["rotations"])
+    c2, _, _ = rast(means3D=loc["means3D"].detach(), means2D=torch.zeros_like(lm2), opacities=loc["opacities"].detach(),
+                    colors_precomp=mask_col, scales=loc["scales"].detach(), rotations=loc["rotations"].detach())
+    (c1 * dL).sum().backward()
+    ref_c2, _, _ = GaussianRasterizer(rs)(means3D=full["means3D"].detach(), means2D=torch.zeros_like(m2),
+                                          opacities=full["opacities"].detach(), colors_precomp=full_col,
+                                          scales=full["scales"].detach(), rotations=full["rotations"].detach())
+    two_ok = torch.equal(c1, color) and torch.equal(c2, ref_c2)
+    del c1, c2
     if a.p2p:  # second round through the recycled peer workspace
         for v in list(loc.values()) + [lm2]:
             v.grad = None
@@ -61,7 +80,7 @@ def main():
                                       scales=loc["scales"], rotations=loc["rotations"])
         (scolor * dL).sum().backward()
         torch.cuda.synchronize()
-    ok = torch.equal(scolor, color) and torch.equal(sdepth, depth) and torch.equal(sradii, S.shard_slice(radii, plan))
+    ok = two_ok and torch.equal(scolor, color) and torch.equal(sdepth, depth) and torch.equal(sradii, S.shard_slice(radii, plan))
     worst = 0.0
     pairs = [(loc[k].grad, S.shard_slice(full[k].grad, plan)) for k in loc] + [(lm2.grad, S.shard_slice(m2.grad, plan))]
     for g, w in pairs:
