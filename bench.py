@@ -61,16 +61,47 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed region (B200_PROFILING.md recipe). NVML is polled from a thread every
+    ~4 ms (a timed region of K steps lasts only K x 1.4 ms); if NVML is unavailable, `nvidia-smi -lms 100` is used."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, gpu_index):
         self.rows = []
         self.proc = None
         self.gpu = gpu_index
+        self.nvml = None
+        self.stop_flag = False
+
+    def _nvml_loop(self):
+        nv, h = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), int(mask)))
+            except Exception:
+                break
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nvml = (nv, h)
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -85,6 +116,13 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1.0)
+            sm = [r[0] for r in self.rows]
+            reasons = sorted(n for n, b in self.BITS.items() if any(r[1] & b for r in self.rows))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -103,7 +141,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def to_dev(a, dev):
@@ -134,17 +172,26 @@ class Workload:
 
     def stage_host_inputs(self, k):
         """e2e leg: this step's inputs travel from pinned host memory inside the timed region. The camera (144 B) goes
-        on the compute stream; the 23 MB G image is only needed by the loss, so it is copied on a side stream into a
-        fresh buffer and overlaps whatever the GPU is doing when the host issues it (the tail of the previous step and
-        this step's forward); the compute stream waits for it right before the loss. The copy takes 0.42 ms at
-        the measured 54 GB/s (`e2e.h2d_GBps_measured`); ordering it behind the previous step's backward, as an earlier
-        version did, exposed part of it (1.54 instead of 1.43 ms per step)."""
+        on the compute stream; the 23 MB G image is only needed by the loss, so it is copied on a side stream into one
+        of two persistent device buffers and overlaps whatever the GPU is doing when the host issues it (the tail of
+        the previous step and this step's forward); the compute stream waits for it right before the loss. The copy
+        takes 0.42 ms at the measured 54 GB/s (`e2e.h2d_GBps_measured`). A buffer is reused only after the backward
+        that read it (two steps earlier) has finished -- an event, not an allocation, guards it: per-step allocation
+        of the image on the side stream made the caching allocator stall once the run got longer than ~50 steps."""
         cur = torch.cuda.current_stream(self.dev)
         blob = self.cam_host[k].to(self.dev, non_blocking=True)
+        if not hasattr(self, "_G_dev"):
+            self._G_dev = [torch.empty_like(self.G) for _ in range(2)]
+            self._G_free = [None, None]
+            self._slot = 0
+        slot = self._slot
+        self._slot ^= 1
         with torch.cuda.stream(self.copy_stream):
-            G = self.G_host.to(self.dev, non_blocking=True)
-        G.record_stream(cur)
-        return blob, G
+            if self._G_free[slot] is not None:
+                self.copy_stream.wait_event(self._G_free[slot])
+            self._G_dev[slot].copy_(self.G_host, non_blocking=True)
+        self._cur_slot = slot
+        return blob, self._G_dev[slot]
 
     def join_host_inputs(self):
         torch.cuda.current_stream(self.dev).wait_stream(self.copy_stream)
@@ -160,6 +207,7 @@ class Workload:
         buf.copy_(loss.detach().reshape(1), non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.dev))
+        self._G_free[self._cur_slot] = ev   # forward, loss and backward of this step are behind this event
         return PendingLoss(buf, ev)
 
 
@@ -299,7 +347,7 @@ def alg_bytes(desc, M, Msh, W, H):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c3")
