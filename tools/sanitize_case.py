@@ -1,0 +1,75 @@
+"""Tiny end-to-end scenario for compute-sanitizer (memcheck / racecheck): every kernel family on a small cloud.
+
+    compute-sanitizer --tool memcheck python tools/sanitize_case.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from gaussianeditor_b200 import _lib, sharded as S, synth  # noqa: E402
+from gaussianeditor_b200.rasterizer import GaussianRasterizer  # noqa: E402
+from util import cloud_tensors, run_ours, settings_from  # noqa: E402
+
+dev = torch.device("cuda")
+cloud, _ = synth.make_config("c3", P=3001)
+cam = synth.ring_cameras(8, 4.5, 15.0, 200, 136, 61.0)[2]   # partial last tile column and row
+dL = np.random.default_rng(0).uniform(size=(3, cam.image_height, cam.image_width)).astype(np.float32)
+
+for fv in (0, 1, 2, 3, 4, 5):
+    _lib.set_option("render_fwd_variant", fv)
+    run_ours(cloud, cam, (0.1, 0.2, 0.3))
+_lib.set_option("render_fwd_variant", 3)
+for bv in (0, 1, 2, 3, 4, 6, 7, 8):
+    _lib.set_option("render_bwd_variant", bv)
+    run_ours(cloud, cam, (0.1, 0.2, 0.3), dL=dL)
+_lib.set_option("render_bwd_variant", 4)
+run_ours(cloud, cam, (0, 0, 0), dL=dL, colors_precomp=np.random.default_rng(1).random((3001, 3), dtype=np.float32))
+for M, deg in ((9, 2), (4, 1), (1, 0)):                      # non-TMA SH paths
+    c2 = synth.Cloud(means3D=cloud.means3D, scales=cloud.scales, rotations=cloud.rotations, opacities=cloud.opacities,
+                     shs=np.ascontiguousarray(cloud.shs[:, :M]), sh_degree=deg)
+    run_ours(c2, cam, (0, 0, 0), dL=dL)
+
+# semantic tracing + markVisible
+rs = settings_from(cam, (0, 0, 0), cloud.sh_degree, dev)
+rast = GaussianRasterizer(rs)
+ct = cloud_tensors(cloud, dev)
+w = torch.zeros(3001, 1, device=dev); cnt = torch.zeros(3001, 1, dtype=torch.int32, device=dev)
+rast.apply_weights(ct["means3D"], torch.zeros_like(ct["means3D"]), ct["opacities"], None, w, ct["scales"], ct["rotations"], None,
+                   cnt, (torch.rand(1, cam.image_height, cam.image_width, device=dev) > 0.5).float())
+rast.markVisible(ct["means3D"])
+
+# fused activations (bulk block path needs P % 4 == 0 rows in the last block: run both)
+for P in (3001, 3072):
+    cl, _ = synth.make_config("c3", P=P)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    op = t(cl.opacities).clamp(1e-6, 1 - 1e-6)
+    raw = [t(cl.means3D), torch.zeros(P, 3, device=dev), torch.log(op / (1 - op)), t(cl.shs[:, :1]).contiguous(),
+           t(cl.shs[:, 1:]).contiguous(), torch.log(t(cl.scales)), t(cl.rotations) * 2.0]
+    raw = [x.requires_grad_(True) for x in raw]
+    col, _, _ = rast.forward_raw(*raw)
+    (col * torch.from_numpy(dL).to(dev)).sum().backward()
+
+# Gaussian-sharded path, two virtual ranks on this GPU
+empty = torch.empty(0, device=dev)
+plans = [S.ShardPlan(3001, 2, r) for r in range(2)]
+geom = radii = None
+bufs = []
+for p in plans:
+    sl = lambda x: S.shard_slice(x, p)
+    b = S.shard_preprocess(p, rs, sl(ct["means3D"]), sl(ct["shs"]), empty, sl(ct["opacities"]), sl(ct["scales"]),
+                           sl(ct["rotations"]), empty, geom=geom, radii=radii)
+    geom, radii = b.geom, b.radii
+    bufs.append(b)
+for b in bufs:   # the ranks run one after the other on the shared arrays (no clone: keeps initcheck quiet)
+    S.shard_order(b)
+    frame = torch.zeros(4, cam.image_height, cam.image_width, device=dev)
+    S.shard_render(b, frame[:3], frame[3:])
+    acc = S.shard_backward_render(b, torch.from_numpy(dL).to(dev))
+    S.shard_backward_preprocess(b, acc[b.plan.base:b.plan.base + b.plan.slice_len].contiguous())
+torch.cuda.synchronize()
+print("SANITIZE_CASE_DONE")
