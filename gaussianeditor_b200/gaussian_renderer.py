@@ -15,27 +15,51 @@ import torch
 
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 
-C0 = 0.28209479177387814
+
+def _settings_for(cam, bg_color, scale_modifier, sh_degree) -> GaussianRasterizationSettings:
+    """The camera -> settings mapping both entry points share (FoV -> tangent, transposed matrices as stored by
+    scene/cameras.py:92-94)."""
+    fields = dict(image_height=int(cam.image_height), image_width=int(cam.image_width),
+                  tanfovx=math.tan(0.5 * cam.FoVx), tanfovy=math.tan(0.5 * cam.FoVy), bg=bg_color,
+                  scale_modifier=scale_modifier, viewmatrix=cam.world_view_transform,
+                  projmatrix=cam.full_proj_transform, sh_degree=sh_degree, campos=cam.camera_center,
+                  prefiltered=False, debug=False)
+    return GaussianRasterizationSettings(**fields)
 
 
 def camera2rasterizer(viewpoint_camera, bg_color: torch.Tensor, sh_degree: int = 0):
-    tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
-    tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
-    raster_settings = GaussianRasterizationSettings(
-        image_height=int(viewpoint_camera.image_height),
-        image_width=int(viewpoint_camera.image_width),
-        tanfovx=tanfovx,
-        tanfovy=tanfovy,
-        bg=bg_color,
-        scale_modifier=1.0,
-        viewmatrix=viewpoint_camera.world_view_transform,
-        projmatrix=viewpoint_camera.full_proj_transform,
-        sh_degree=sh_degree,
-        campos=viewpoint_camera.camera_center,
-        prefiltered=False,
-        debug=False,
-    )
-    return GaussianRasterizer(raster_settings=raster_settings)
+    return GaussianRasterizer(raster_settings=_settings_for(viewpoint_camera, bg_color, 1.0, sh_degree))
+
+
+def _sh_basis(deg: int, d: torch.Tensor) -> torch.Tensor:
+    """Real SH basis up to degree 3 at unit directions d [P,3] -> [P,(deg+1)^2], the reference's constants and signs
+    (utils/sh_utils.py / cuda_rasterizer/forward.cu:20-71)."""
+    x, y, z = d[:, 0], d[:, 1], d[:, 2]
+    cols = [torch.full_like(x, 0.28209479177387814)]
+    if deg >= 1:
+        c1 = 0.4886025119029199
+        cols += [-c1 * y, c1 * z, -c1 * x]
+    if deg >= 2:
+        xx, yy, zz = x * x, y * y, z * z
+        cols += [1.0925484305920792 * x * y, -1.0925484305920792 * y * z, 0.31539156525252005 * (2 * zz - xx - yy),
+                 -1.0925484305920792 * x * z, 0.5462742152960396 * (xx - yy)]
+    if deg >= 3:
+        cols += [-0.5900435899266435 * y * (3 * xx - yy), 2.890611442640554 * x * y * z,
+                 -0.4570457994644658 * y * (4 * zz - xx - yy), 0.3731763325901154 * z * (2 * zz - 3 * xx - 3 * yy),
+                 -0.4570457994644658 * x * (4 * zz - xx - yy), 1.445305721320277 * z * (xx - yy),
+                 -0.5900435899266435 * x * (xx - 3 * yy)]
+    return torch.stack(cols, dim=1)
+
+
+def _python_sh_colors(pc, camera_center) -> torch.Tensor:
+    """``pipe.convert_SHs_python``: evaluate the SH colour in PyTorch and hand it over as precomputed colour
+    (gaussian_renderer/__init__.py:103-121): clamp_min(sum_k basis_k * sh_k + 0.5, 0)."""
+    feats = pc.get_features                                   # [P, M, 3]
+    view = pc.get_xyz - camera_center.reshape(1, 3)
+    view = view / view.norm(dim=1, keepdim=True)
+    basis = _sh_basis(pc.active_sh_degree, view)              # [P, nb]
+    rgb = torch.einsum("pk,pkc->pc", basis, feats[:, :basis.shape[1], :])
+    return torch.clamp_min(rgb + 0.5, 0.0)
 
 
 def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=1.0, override_color=None,
@@ -48,79 +72,36 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     sigmoid / exp / normalize and reads the SH row from the two feature arrays inside its preprocess kernels: the
     per-render PyTorch prologue (five elementwise kernels, a [P,16,3] ``torch.cat``) and its autograd epilogue go away.
     Only valid for the plain SH path (no override colour, no Python-side SH / covariance)."""
-    screenspace_points = torch.zeros_like(pc.get_xyz, dtype=pc.get_xyz.dtype, requires_grad=True,
-                                          device=pc.get_xyz.device) + 0
+    xyz = pc.get_xyz
+    # gradient sink for the 2-D means: densification reads its .grad (gaussian_renderer/__init__.py:60-69)
+    screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
     try:
         screenspace_points.retain_grad()
     except Exception:
         pass
+    rasterizer = GaussianRasterizer(
+        raster_settings=_settings_for(viewpoint_camera, bg_color, scaling_modifier, pc.active_sh_degree))
+    python_sh = getattr(pipe, "convert_SHs_python", False)
+    python_cov = getattr(pipe, "compute_cov3D_python", False)
 
-    tanfovx = math.tan(viewpoint_camera.FoVx * 0.5)
-    tanfovy = math.tan(viewpoint_camera.FoVy * 0.5)
-    raster_settings = GaussianRasterizationSettings(
-        image_height=int(viewpoint_camera.image_height),
-        image_width=int(viewpoint_camera.image_width),
-        tanfovx=tanfovx,
-        tanfovy=tanfovy,
-        bg=bg_color,
-        scale_modifier=scaling_modifier,
-        viewmatrix=viewpoint_camera.world_view_transform,
-        projmatrix=viewpoint_camera.full_proj_transform,
-        sh_degree=pc.active_sh_degree,
-        campos=viewpoint_camera.camera_center,
-        prefiltered=False,
-        debug=False,
-    )
-    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
-
-    means3D = pc.get_xyz
-    means2D = screenspace_points
     if fused_activations:
-        if override_color is not None or getattr(pipe, "convert_SHs_python", False) or \
-                getattr(pipe, "compute_cov3D_python", False):
+        if override_color is not None or python_sh or python_cov:
             raise ValueError("fused_activations needs the plain SH + scale/rotation path")
-        rendered_image, radii, depth = rasterizer.forward_raw(
-            means3D=means3D, means2D=means2D, opacity_logits=pc._opacity, features_dc=pc._features_dc,
+        image, radii, depth = rasterizer.forward_raw(
+            means3D=xyz, means2D=screenspace_points, opacity_logits=pc._opacity, features_dc=pc._features_dc,
             features_rest=pc._features_rest, log_scales=pc._scaling, raw_rotations=pc._rotation)
-        return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
-                "radii": radii, "depth_3dgs": depth}
-    opacity = pc.get_opacity
-
-    scales = rotations = cov3D_precomp = None
-    if getattr(pipe, "compute_cov3D_python", False):
-        cov3D_precomp = pc.get_covariance(scaling_modifier)
     else:
-        scales = pc.get_scaling
-        rotations = pc.get_rotation
-
-    shs = colors_precomp = None
-    if override_color is None:
-        if getattr(pipe, "convert_SHs_python", False):
-            from .sh_utils import eval_sh
-            shs_view = pc.get_features.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
-            dir_pp = pc.get_xyz - viewpoint_camera.camera_center.repeat(pc.get_features.shape[0], 1)
-            dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
-            sh2rgb = eval_sh(pc.active_sh_degree, shs_view, dir_pp_normalized)
-            colors_precomp = torch.clamp_min(sh2rgb + 0.5, 0.0)
+        kw = dict(means3D=xyz.float(), means2D=screenspace_points.float(), opacities=pc.get_opacity.float())
+        if python_cov:
+            kw["cov3D_precomp"] = pc.get_covariance(scaling_modifier)
         else:
-            shs = pc.get_features.float()
-    else:
-        colors_precomp = override_color
-
-    rendered_image, radii, depth = rasterizer(
-        means3D=means3D.float(),
-        means2D=means2D.float(),
-        shs=shs,
-        colors_precomp=colors_precomp,
-        opacities=opacity.float(),
-        scales=None if scales is None else scales.float(),
-        rotations=None if rotations is None else rotations.float(),
-        cov3D_precomp=cov3D_precomp,
-    )
-    return {
-        "render": rendered_image,
-        "viewspace_points": screenspace_points,
-        "visibility_filter": radii > 0,
-        "radii": radii,
-        "depth_3dgs": depth,
-    }
+            kw.update(scales=pc.get_scaling.float(), rotations=pc.get_rotation.float())
+        if override_color is not None:
+            kw["colors_precomp"] = override_color
+        elif python_sh:
+            kw["colors_precomp"] = _python_sh_colors(pc, viewpoint_camera.camera_center)
+        else:
+            kw["shs"] = pc.get_features.float()
+        image, radii, depth = rasterizer(**kw)
+    return {"render": image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0, "radii": radii,
+            "depth_3dgs": depth}

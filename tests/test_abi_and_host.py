@@ -146,3 +146,38 @@ def test_shard_entry_points_validate_before_touching_the_device():
     assert lib.gsr_shard_preprocess_p2p(C.byref(s), C.byref(shard), 100, 0, 10, peers, 2, 2, 1 << 20, dummy, None) == -1
     ev = _lib.ExchangeView()
     assert lib.gsr_view_exchange(dummy, -1, C.byref(ev)) == -1
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_python_sh_colour_path_of_render_mirror(deg):
+    """render()'s ``pipe.convert_SHs_python`` branch (gaussian_renderer.py:_python_sh_colors) against an independent
+    restatement of the reference's eval_sh (tests/test_oracle_kat.py)."""
+    from types import SimpleNamespace
+    from gaussianeditor_b200 import gaussian_renderer as GR
+    from test_oracle_kat import _eval_sh_numpy
+    g = torch.Generator().manual_seed(deg)
+    P = 40
+    xyz = torch.randn(P, 3, generator=g, dtype=torch.float64)
+    feats = torch.randn(P, 16, 3, generator=g, dtype=torch.float64)
+    campos = torch.tensor([0.3, -1.0, 2.0], dtype=torch.float64)
+    pc = SimpleNamespace(get_features=feats, get_xyz=xyz, active_sh_degree=deg)
+    got = GR._python_sh_colors(pc, campos).numpy()
+    d = (xyz - campos).numpy()
+    d = d / np.linalg.norm(d, axis=1, keepdims=True)
+    sh = feats.numpy().transpose(0, 2, 1)                                # [P, 3, M] like the reference's shs_view
+    want = np.maximum(_eval_sh_numpy(deg, sh, d) + 0.5, 0.0)
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under gaussianeditor_b200/ or diff_gaussian_rasterization/ may
+    import, load or execute it (no CPU fallback can hide behind the product path)."""
+    bad = []
+    for top in ("gaussianeditor_b200", "diff_gaussian_rasterization"):
+        for dp, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    text = open(os.path.join(dp, f), errors="replace").read()
+                    if re.search(r"^\s*(from|import)\s+oracle\b|oracle/_ref|cpu_oracle|liboracle|libdgr_ref", text, re.M):
+                        bad.append(os.path.join(dp, f))
+    assert bad == []
