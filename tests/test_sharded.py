@@ -175,3 +175,30 @@ def test_two_process_nccl_matches_single_gpu(p2p):
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_CHECK_OK" in r.stdout
+
+
+def test_workspace_pool_hands_out_distinct_workspaces_in_a_fixed_order():
+    """Host logic of the pooled step workspaces (CPU tensors): forwards that are alive at the same time never share
+    a workspace, released workspaces are reused lowest index first (what keeps peer workspaces paired across ranks),
+    and scratch buffers persist and only grow."""
+    import gc
+    import weakref
+    pool = S.WorkspacePool(exchange=None, geometry_bytes=1024, p2p=False)
+    dev = torch.device("cpu")
+
+    class Holder:   # stands in for the ShardBuffers of one forward
+        pass
+    a, b = Holder(), Holder()
+    wa, wb = pool.take(dev), pool.take(dev)
+    weakref.finalize(a, pool.give, wa); weakref.finalize(b, pool.give, wb)
+    assert wa is not wb and (wa.index, wb.index) == (0, 1) and len(pool.all) == 2
+    t1 = wa.get("binning", 1000, torch.uint8, grow=1.25)
+    assert t1.numel() == 1000 and wa.get("binning", 900, torch.uint8).data_ptr() == t1.data_ptr()   # reused, not re-allocated
+    big = wa.get("binning", 5000, torch.uint8, grow=1.25)
+    assert big.numel() == 5000 and wa.bufs["binning"].numel() >= 6250                                # grew with headroom
+    del b; gc.collect()
+    del a; gc.collect()
+    assert [w.index for w in pool.free] == [0, 1]            # released in the other order, still sorted by index
+    assert pool.take(dev) is wa and pool.take(dev) is wb and len(pool.all) == 2
+    pool.close()
+    assert pool.all == [] and pool.free == []
