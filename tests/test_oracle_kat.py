@@ -261,3 +261,39 @@ def test_apply_weights_counts():
     assert np.array_equal(w[:, 0], cnt[:, 0].astype(np.float32))
     assert cnt.sum() == f.hits
     assert cnt[f.radii == 0].sum() == 0
+
+
+def test_precomputed_colour_and_covariance_paths_of_the_oracle():
+    """The two alternative input paths (Appendix A item 16: colors_precomp is live in GaussianEditor's mask render;
+    cov3D_precomp is never used there but part of the API): precomputed inputs that equal what the oracle derives
+    itself must give the same image, and the colour gradient must be the plain blending weight sum (closed form:
+    dL/dcolor_i = sum_pixels alpha_i * T_i * G), independent of the SH machinery."""
+    cloud, cams = synth.make_config("c3", P=1500)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 112, 80, 61.0)[3]
+    bg = (0.2, 0.4, 0.1)
+    base = O.forward_from(cloud, cam, bg, f32=False)
+    vis = base.radii > 0
+    # colours: feed the oracle's own SH->RGB result back as precomputed colours
+    rgb = np.where(vis[:, None], base.rgb, 0.0).astype(np.float32)
+    pc = O.forward_from(cloud, cam, bg, f32=False, colors_precomp=rgb)
+    assert np.array_equal(pc.radii, base.radii) and np.array_equal(pc.point_list, base.point_list)
+    assert np.allclose(pc.color, base.color, atol=2e-7)        # rgb went through float32 once
+    # covariance: feed cov3D back
+    cov = np.where(vis[:, None], base.cov3D, 0.0).astype(np.float32)
+    cv = O.forward_from(cloud, cam, bg, f32=False, cov3D_precomp=cov, scales=None, rotations=None)
+    assert (cv.radii != base.radii).mean() <= 2e-3            # cov3D rounded to float32 moves a radius step rarely
+    same = cv.radii == base.radii
+    assert np.allclose(cv.conic_opacity[same & vis], base.conic_opacity[same & vis], rtol=2e-4, atol=1e-9)
+    # colour gradient is linear in G with the blending weights as coefficients: doubling G doubles it exactly, and a
+    # one-hot G on a pixel gives alpha*T of the splats that cover it, which sum with final_T to 1 (energy conservation)
+    H, W = cam.image_height, cam.image_width
+    G = np.zeros((3, H, W), np.float32)
+    py, px = H // 2, W // 2
+    G[0, py, px] = 1.0
+    g = pc.backward(G)
+    weights = g["dcolor"][:, 0]
+    assert np.all(weights >= 0) and abs(weights.sum() + pc.final_T[py, px] - 1.0) <= 1e-9
+    assert np.all(g["dcolor"][:, 1:] == 0)
+    g2 = pc.backward(2.0 * G)
+    assert np.allclose(g2["dcolor"], 2.0 * g["dcolor"], rtol=0, atol=0)
+    base.close(); pc.close(); cv.close()
