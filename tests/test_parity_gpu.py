@@ -507,3 +507,20 @@ def test_fused_activations_match_pytorch_prologue(deg, M, P):
         assert rel_l2(gb[same].cpu().numpy(), ga[same].cpu().numpy()) <= 1e-4, (k, rel_l2(gb[same].cpu().numpy(), ga[same].cpu().numpy()))
     assert rel_l2(m2b.grad[same].cpu().numpy(), m2a.grad[same].cpu().numpy()) <= 1e-4
     assert float(b["features_rest"].grad[rad_b == 0].abs().sum()) == 0.0   # culled rows are written as exact zeros
+
+
+def test_blending_weights_conserve_energy_at_full_size():
+    """Size-independent property at BASELINE config 3 size: with precomputed colours and dL/dpixel = 1 on one channel,
+    dL/dcolor_i is the total blending weight of splat i, and the weights of all splats plus the remaining
+    transmittance of every pixel add up to the number of pixels (sum_i alpha_i T_i + T_final = 1 per pixel)."""
+    cloud, cams = synth.make_config("c3")
+    cam = cams[5]
+    H, W = cam.image_height, cam.image_width
+    dL = np.zeros((3, H, W), np.float32)
+    dL[1] = 1.0
+    cols = np.random.default_rng(4).random((cloud.means3D.shape[0], 3), dtype=np.float32)
+    out = run_ours(cloud, cam, (0.0, 0.0, 0.0), dL=dL, colors_precomp=cols)
+    w = out["grads"]["dcolor"].double()
+    assert float(w.min()) >= 0.0 and float(w[:, 0].abs().sum()) == 0.0 and float(w[:, 2].abs().sum()) == 0.0
+    total = float(w[:, 1].sum()) + float(out["views"]["final_T"].double().sum())
+    assert abs(total - H * W) <= 2e-5 * H * W, (total, H * W)
