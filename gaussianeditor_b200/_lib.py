@@ -25,6 +25,7 @@ SYMBOLS = [
     "gsr_shard_backward_preprocess",
     "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close", "gsr_peer_free", "gsr_shard_preprocess_p2p",
     "gsr_forward_preprocess_raw", "gsr_backward_raw",
+    "gsr_alpha_image", "gsr_backward_alpha",
 ]
 
 
@@ -123,6 +124,11 @@ def load():
     lib.gsr_backward.restype = C.c_int
     lib.gsr_backward.argtypes = [C.POINTER(Settings), C.POINTER(Cloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz,
                                  C.POINTER(Grads), vp]
+    lib.gsr_backward_alpha.restype = C.c_int
+    lib.gsr_backward_alpha.argtypes = [C.POINTER(Settings), C.POINTER(Cloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp,
+                                       sz, C.POINTER(Grads), vp]
+    lib.gsr_alpha_image.restype = C.c_int
+    lib.gsr_alpha_image.argtypes = [vp, sz, i32, i32, vp, vp]
     lib.gsr_mark_visible.restype = C.c_int
     lib.gsr_mark_visible.argtypes = [i32, vp, vp, vp, vp, vp]
     lib.gsr_apply_weights.restype = C.c_int

@@ -2,9 +2,11 @@
 // Orchestration mirrors CudaRasterizer::Rasterizer::{forward,backward,markVisible,apply_weights}
 // (cuda_rasterizer/rasterizer_impl.cu:128-133,179-285,289-341,343-446) with the forward split in two halves
 // around the single host read of num_rendered.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -13,7 +15,7 @@ namespace gsr {
 
 Options g_opt;
 unsigned long long* g_stats_dev = nullptr;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -35,6 +37,7 @@ int check_launch(const char* what, bool debug, cudaStream_t st) {
 
 struct ProfRec { int stage; cudaEvent_t a, b; };
 static std::vector<ProfRec*> g_prof;
+static std::mutex g_prof_mu;  // autograd runs the backward on its own thread while the main thread may be in a forward
 StageScope::StageScope(int stage_, cudaStream_t st_) : stage(stage_), st(st_), rec(nullptr) {
   if (!g_opt.profile) return;
   ProfRec* r = new ProfRec();
@@ -48,6 +51,7 @@ StageScope::~StageScope() {
   if (!rec) return;
   ProfRec* r = (ProfRec*)rec;
   cudaEventRecord(r->b, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   g_prof.push_back(r);
 }
 
@@ -174,10 +178,10 @@ int gsr_forward_render_speculative(const gsr_settings* s, const gsr_cloud* c, in
                              radii, out_color, out_depth, stream);
 }
 
-int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
-                 const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
-                 const int32_t* radii, const float* dL_dout_color, void* scratch, size_t scratch_bytes,
-                 const gsr_grads* gr, void* stream) {
+static int backward_impl(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
+                         const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
+                         const int32_t* radii, const float* dL_dout_color, const float* dL_dout_alpha, void* scratch,
+                         size_t scratch_bytes, const gsr_grads* gr, void* stream) {
   int rc = validate(s, c);
   if (rc) return rc;
   if (!gr || !dL_dout_color) { set_error("grads / dL_dout_color is null"); return GSR_ERR_INVALID; }
@@ -200,12 +204,38 @@ int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t R, const voi
     cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)c->P * ACC_STRIDE * sizeof(float), st);
     if (e != cudaSuccess) return check_cuda(e, "scratch memset");
     if (R > 0) {
-      rc = launch_render_bwd(*s, g, b, im, dL_dout_color, (float*)scratch, st);
+      rc = launch_render_bwd(*s, g, b, im, dL_dout_color, (float*)scratch, st, TileOwner(), dL_dout_alpha);
       if (rc) return rc;
     }
   }
   StageScope t(ST_PRE_BWD, st);
   return launch_preprocess_bwd(*s, *c, g, radii, (const float*)scratch, *gr, st);
+}
+
+int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
+                 const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
+                 const int32_t* radii, const float* dL_dout_color, void* scratch, size_t scratch_bytes,
+                 const gsr_grads* gr, void* stream) {
+  return backward_impl(s, c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, radii,
+                       dL_dout_color, nullptr, scratch, scratch_bytes, gr, stream);
+}
+
+int gsr_backward_alpha(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
+                       const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
+                       const int32_t* radii, const float* dL_dout_color, const float* dL_dout_alpha, void* scratch,
+                       size_t scratch_bytes, const gsr_grads* gr, void* stream) {
+  return backward_impl(s, c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, radii,
+                       dL_dout_color, dL_dout_alpha, scratch, scratch_bytes, gr, stream);
+}
+
+int gsr_alpha_image(const void* image, size_t image_bytes, int32_t W, int32_t H, float* out_alpha, void* stream) {
+  if (W < 0 || H < 0 || !out_alpha || !image) { set_error("alpha_image: bad arguments"); return GSR_ERR_INVALID; }
+  ImageWS im;
+  carve_image(const_cast<void*>(image), W, H, im);
+  if (im.total > image_bytes) { set_error("image workspace too small: %zu < %zu", image_bytes, im.total); return GSR_ERR_WORKSPACE; }
+  const size_t n = (size_t)W * H;
+  if (n == 0) return GSR_OK;
+  return launch_alpha_image(im.final_T, n, out_alpha, (cudaStream_t)stream);
 }
 
 int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
@@ -530,7 +560,7 @@ int gsr_view_binning(const void* binning, int32_t P, int64_t R, int32_t W, int32
   BinningWS b;
   if (!out || !carve_binning(const_cast<void*>(binning), P, R, W, H, b)) return GSR_ERR_INVALID;
   out->point_list = b.point_list; out->tile_keys = b.keys_sorted;
-  out->tile_key_bytes = ((int64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) <= 65536 && g_opt.tile_key_bits == 16) ? 2 : 4;
+  out->tile_key_bytes = ((int64_t)((W + TILE - 1) / TILE) * ((H + TILE - 1) / TILE) < 65536 && g_opt.tile_key_bits == 16) ? 2 : 4;
   return GSR_OK;
 }
 int gsr_view_image(const void* image, int32_t W, int32_t H, gsr_image_view* out) {
@@ -585,6 +615,7 @@ int gsr_profile_read(double* ms_out, int64_t* calls_out) {
   for (int i = 0; i < GSR_NUM_STAGES; i++) { ms_out[i] = 0.0; calls_out[i] = 0; }
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) return check_cuda(e, "profile_read");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
   for (ProfRec* r : g_prof) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, r->a, r->b) == cudaSuccess && r->stage >= 0 && r->stage < GSR_NUM_STAGES) {

@@ -244,7 +244,10 @@ size_t scan_temp_bytes(int P) {
     return n;
   });
 }
-size_t tile_sort_temp_bytes(int64_t R) {
+// R changes with every frame: the CUB size is queried for R rounded up to a 64K bucket (monotone in the item count),
+// so a long session fills a handful of cache entries instead of one per frame.
+size_t tile_sort_temp_bytes(int64_t R_exact) {
+  const int64_t R = (R_exact + 65535) / 65536 * 65536;
   return g_sizes.get(2, R, [&] {
     size_t n = 0, m = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, n, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
@@ -385,8 +388,8 @@ int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculati
   cudaError_t e = cudaMemsetAsync(im.ranges, 0, (size_t)gx * gy * sizeof(uint2), st);
   if (e != cudaSuccess) return check_cuda(e, "ranges memset");
   if (R <= 0) return GSR_OK;
-  // tile ids fit 16 bits for every image up to 4096x4096 (65536 tiles): half the key traffic of the sort
-  if ((int64_t)gx * gy <= 65536 && g_opt.tile_key_bits == 16)
+  // tile ids (and the padding key 2^bit - 1 > Ntile - 1) fit 16 bits up to 65535 tiles: half the key traffic of the sort
+  if ((int64_t)gx * gy < 65536 && g_opt.tile_key_bits == 16)
     return bin_typed<uint16_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug, own);
   return bin_typed<uint32_t>(c, R, speculative, gx, gy, g, b, im, radii, st, debug, own);
 }

@@ -1,6 +1,7 @@
 // Shared declarations of the sm_100a rasterizer kernels (internal; the public surface is include/gsr_b200.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -88,7 +89,7 @@ struct StageScope {
 };
 extern Options g_opt;
 extern unsigned long long* g_stats_dev;  // device counters when option "stats" is on (instrumentation only)
-extern long long g_launches;
+extern std::atomic<long long> g_launches;
 
 // ---- error plumbing ------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
@@ -113,7 +114,8 @@ int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculati
 int launch_render_fwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
                       float* out_color, float* out_depth, cudaStream_t st, const TileOwner& own = TileOwner());
 int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
-                      const float* dL_dpix, float* acc, cudaStream_t st, const TileOwner& own = TileOwner());
+                      const float* dL_dpix, float* acc, cudaStream_t st, const TileOwner& own = TileOwner(),
+                      const float* dL_dalpha_img = nullptr);
 // raw != nullptr: RAW variant -- gradients w.r.t. the raw parameters (gr.dL_dsh = d features_dc, raw->dL_dfeatures_rest)
 struct RawBackward {
   const float* features_rest;
@@ -121,6 +123,8 @@ struct RawBackward {
 };
 int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
                           const float* acc, const gsr_grads& gr, cudaStream_t st, const RawBackward* raw = nullptr);
+// out_alpha[i] = 1 - final_T[i]  (the reference keeps final_T as ImageState::accum_alpha, rasterizer_impl.h:50)
+int launch_alpha_image(const float* final_T, size_t n, float* out_alpha, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);
 int launch_apply_weights(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
                          const float* image_weights, int CH, float* weights, int32_t* cnt, cudaStream_t st);

@@ -37,6 +37,7 @@ struct BwdArgs {
   const float* final_T;
   const uint32_t* n_contrib;
   const float* dL_dpix;
+  const float* dL_dalpha_img;  // optional [H*W]: gradient of the alpha image 1 - final_T (gsr_backward_alpha)
   float* acc;  // [P, ACC_STRIDE]
   int own_stride, own_phase;  // tile-row ownership (1, 0 = all tiles)
 };
@@ -52,6 +53,14 @@ struct BwdArgs {
 struct PixState {
   float T, ar, d0, d1, d2, bgT;   // ar = accum_rec . dL_dpixel (scalar; see hit_update)
 };
+
+// What multiplies dT_final/dalpha_i = -T_final/(1-alpha_i) in dL/dalpha_i: the background term of the colour
+// (backward.cu:505-511: bg . dL_dpixel) and, when the caller asked for the alpha image A = 1 - T_final, -dL/dA.
+__device__ __forceinline__ float bg_term(const BwdArgs& a, size_t pix_id, float bg0, float bg1, float bg2, const PixState& p) {
+  float t = bg0 * p.d0 + bg1 * p.d1 + bg2 * p.d2;
+  if (a.dL_dalpha_img != nullptr) t -= a.dL_dalpha_img[pix_id];
+  return t;
+}
 
 __device__ __forceinline__ void hit_update(PixState& p, float* g, float dx, float dy, float G, float alpha, float o,
                                            float c0, float c1, float c2) {
@@ -198,7 +207,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32) render_bwd_warp_kernel(const Bw
       p.d0 = a.dL_dpix[pix_id];
       p.d1 = a.dL_dpix[HW + pix_id];
       p.d2 = a.dL_dpix[2 * HW + pix_id];
-      p.bgT = Tf * (bg0 * p.d0 + bg1 * p.d1 + bg2 * p.d2);
+      p.bgT = Tf * bg_term(a, pix_id, bg0, bg1, bg2, p);
       nc[k] = a.n_contrib[pix_id];
     }
     ps[k] = p;
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
       p.d0 = a.dL_dpix[pix_id];
       p.d1 = a.dL_dpix[HW + pix_id];
       p.d2 = a.dL_dpix[2 * HW + pix_id];
-      p.bgT = Tf * (bg0 * p.d0 + bg1 * p.d1 + bg2 * p.d2);
+      p.bgT = Tf * bg_term(a, pix_id, bg0, bg1, bg2, p);
       nc[k] = a.n_contrib[pix_id];
     }
     ps[k] = p;
@@ -467,7 +476,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs 
     const float Tf = a.final_T[pix_id];
     p.T = Tf;
     p.d0 = a.dL_dpix[pix_id]; p.d1 = a.dL_dpix[HW + pix_id]; p.d2 = a.dL_dpix[2 * HW + pix_id];
-    p.bgT = Tf * (a.bg[0] * p.d0 + a.bg[1] * p.d1 + a.bg[2] * p.d2);
+    p.bgT = Tf * bg_term(a, pix_id, a.bg[0], a.bg[1], a.bg[2], p);
     nc = a.n_contrib[pix_id];
   }
   const float ddelx_dx = 0.5f * a.W, ddely_dy = 0.5f * a.H;
@@ -514,8 +523,10 @@ __global__ void __launch_bounds__(TILE_PIX) render_bwd_cta_kernel(const BwdArgs 
 }  // namespace
 
 int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
-                      const float* dL_dpix, float* acc, cudaStream_t st, const TileOwner& own) {
+                      const float* dL_dpix, float* acc, cudaStream_t st, const TileOwner& own,
+                      const float* dL_dalpha_img) {
   BwdArgs a;
+  a.dL_dalpha_img = dL_dalpha_img;
   a.own_stride = own.stride; a.own_phase = own.phase;
   a.ranges = im.ranges; a.point_list = b.point_list; a.records = g.records; a.tile_last = im.tile_last;
   a.W = s.image_width; a.H = s.image_height;

@@ -57,13 +57,20 @@ def _ptr(t):
     return None if t is None or t.numel() == 0 else C.c_void_p(t.data_ptr())
 
 
+def _bounded_put(d: dict, key, value, limit: int = 64):
+    """Densification changes P every few hundred steps: keep the per-(P, W, H) dictionaries from growing forever."""
+    if key not in d and len(d) >= limit:
+        d.pop(next(iter(d)))
+    d[key] = value
+
+
 def _geometry_bytes(lib, P):
     key = ("g", P)
     if key not in _size_cache:
         n = lib.gsr_geometry_bytes(P)
         if n == 0:
             _lib.check(-2, "gsr_geometry_bytes")
-        _size_cache[key] = n
+        _bounded_put(_size_cache, key, n)
     return _size_cache[key]
 
 
@@ -174,7 +181,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
                                                   _ptr(state.binning), bbytes, _ptr(state.img), ibytes,
                                                   _ptr(state.radii), _ptr(color), _ptr(depth), st), "gsr_forward_render")
         if P > 0:
-            _r_hint[key] = max(R, int(0.9 * _r_hint.get(key, 0)))
+            _bounded_put(_r_hint, key, max(R, int(0.9 * _r_hint.get(key, 0))))
     inputs = (means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp)
     if raw:
         inputs = inputs + (raw_rest,)
@@ -182,15 +189,25 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
+                        raster_settings, return_alpha=False):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
-                                     cov3Ds_precomp, raster_settings)
+                                     cov3Ds_precomp, raster_settings, return_alpha)
+
+
+def _alpha_image(lib, state, device):
+    """alpha = 1 - final_T as a [1,H,W] tensor (gsr_alpha_image; final_T is the reference's accum_alpha)."""
+    alpha = torch.zeros(1, state.H, state.W, dtype=torch.float32, device=device)
+    if state.P > 0 and state.W * state.H > 0:
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.gsr_alpha_image(_ptr(state.img), state.img.numel(), state.W, state.H, _ptr(alpha), st),
+                   "gsr_alpha_image")
+    return alpha
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings):
+                raster_settings, return_alpha=False):
         color, depth, state, inputs = _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations,
                                                     cov3Ds_precomp, raster_settings)
         ctx.raster_settings = raster_settings
@@ -198,10 +215,13 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.save_for_backward(*inputs, state.radii, state.geom, state.binning, state.img)
         ctx.mark_non_differentiable(state.radii)
         _RasterizeGaussians.last_state = state  # for parity tests / instrumentation only
+        if return_alpha:   # opt-in fourth output (not in the reference's tuple): alpha = 1 - final_T, differentiable
+            with torch.cuda.device(means3D.device):
+                return color, state.radii, depth, _alpha_image(_lib.load(), state, means3D.device)
         return color, state.radii, depth
 
     @staticmethod
-    def backward(ctx, grad_out_color, grad_radii, grad_depth):
+    def backward(ctx, grad_out_color, grad_radii, grad_depth, grad_alpha=None):
         lib = _lib.load()
         rs = ctx.raster_settings
         state = ctx.state
@@ -225,15 +245,22 @@ class _RasterizeGaussians(torch.autograd.Function):
                 gr = _lib.Grads(_ptr(dL_dmeans3D), _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity),
                                 _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
                 st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-                _lib.check(lib.gsr_backward(C.byref(s), C.byref(c), state.cap, _ptr(geom), geom.numel(),
-                                            _ptr(binning), binning.numel(), _ptr(img), img.numel(), _ptr(radii),
-                                            _ptr(grad_out_color), _ptr(scratch), sbytes, C.byref(gr), st),
-                           "gsr_backward")
+                if grad_alpha is not None:
+                    grad_alpha = _f32c(grad_alpha, device)
+                    _lib.check(lib.gsr_backward_alpha(C.byref(s), C.byref(c), state.cap, _ptr(geom), geom.numel(),
+                                                      _ptr(binning), binning.numel(), _ptr(img), img.numel(),
+                                                      _ptr(radii), _ptr(grad_out_color), _ptr(grad_alpha),
+                                                      _ptr(scratch), sbytes, C.byref(gr), st), "gsr_backward_alpha")
+                else:
+                    _lib.check(lib.gsr_backward(C.byref(s), C.byref(c), state.cap, _ptr(geom), geom.numel(),
+                                                _ptr(binning), binning.numel(), _ptr(img), img.numel(), _ptr(radii),
+                                                _ptr(grad_out_color), _ptr(scratch), sbytes, C.byref(gr), st),
+                               "gsr_backward")
                 if scales.numel() == 0:  # cov3D_precomp path: the reference leaves these at their zero-fill
                     dL_dscales.zero_(); dL_drotations.zero_()
         # same slots as the reference (__init__.py:213-223); autograd drops grads of inputs that do not need one
         return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,
-                None)
+                None, None)
 
 
 class _RasterizeGaussiansRaw(torch.autograd.Function):
@@ -283,9 +310,13 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings):
+    def __init__(self, raster_settings, return_alpha: bool = False):
+        """``return_alpha=True`` (opt-in, not in the reference) appends a fourth output to ``forward``: the alpha image
+        ``1 - final_T`` [1,H,W] (the reference keeps final_T as ``accum_alpha`` but never returns it); it is
+        differentiable like the colour."""
         super().__init__()
         self.raster_settings = raster_settings
+        self.return_alpha = bool(return_alpha)
 
     def forward_raw(self, means3D, means2D, opacity_logits, features_dc, features_rest, log_scales, raw_rotations):
         """Opt-in fused-activation call (not part of the reference API): the arguments are the scene model's raw
@@ -336,7 +367,7 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = empty
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, raster_settings)
+                                   cov3D_precomp, raster_settings, self.return_alpha)
 
     def apply_weights(self, means3D, means2D, opacities, shs=None, weights=None, scales=None, rotations=None,
                       cov3Ds_precomp=None, cnt=None, image_weights=None):

@@ -428,7 +428,9 @@ class _ShardedRasterize(torch.autograd.Function):
         shard_render(buf, frame[:3], frame[3:])
         exchange.all_reduce_sum(frame)
         ctx.buf, ctx.exchange = buf, exchange
-        radii = shard_slice(buf.radii, plan)
+        # a fresh tensor, like the single-GPU path and the reference: buf.radii lives in the pooled StepWorkspace and is
+        # overwritten by the next forward that takes that workspace
+        radii = shard_slice(buf.radii, plan).clone()
         ctx.mark_non_differentiable(radii)
         _ShardedRasterize.last_R = buf.R  # instrumentation only (no reference to the buffers: they must be free to die)
         return frame[:3], radii, frame[3:]

@@ -136,6 +136,20 @@ GSR_API int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t num_
                  size_t image_bytes, const int32_t* radii, const float* dL_dout_color, void* scratch,
                  size_t scratch_bytes, const gsr_grads* grads, void* stream);
 
+/* ---- alpha image (north-star output "RGB / depth / alpha"; opt-in, not in the reference's return tuple) ----
+ * out_alpha [H*W] = 1 - final_T, where final_T is what the reference keeps as ImageState::accum_alpha
+ * (cuda_rasterizer/rasterizer_impl.h:50, written at forward.cu:371-378). Call after gsr_forward_render on the same
+ * `image` workspace. gsr_backward_alpha is gsr_backward with the additional upstream gradient dL_dout_alpha [H*W]
+ * (NULL = none): d(1 - T_final)/d(alpha_i) = T_final / (1 - alpha_i) enters dL/dalpha_i next to the background term
+ * of backward.cu:505-511. */
+GSR_API int gsr_alpha_image(const void* image, size_t image_bytes, int32_t image_width, int32_t image_height,
+                    float* out_alpha, void* stream);
+GSR_API int gsr_backward_alpha(const gsr_settings* s, const gsr_cloud* c, int32_t num_rendered, const void* geometry,
+                       size_t geometry_bytes, const void* binning, size_t binning_bytes, const void* image,
+                       size_t image_bytes, const int32_t* radii, const float* dL_dout_color,
+                       const float* dL_dout_alpha, void* scratch, size_t scratch_bytes, const gsr_grads* grads,
+                       void* stream);
+
 /* ---- markVisible: present[i] = view-space z > 0.2 (auxiliary.h:139-164) ------------------------------- */
 GSR_API int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);

@@ -119,7 +119,7 @@ def test_forward_backward_vs_cpu_oracle():
         g = f.backward(dL)
         for a, b in [("dmean3D", "dmean3D"), ("dmean2D", "dmean2D"), ("dopacity", "dopacity"), ("dscale", "dscale"),
                      ("drot", "drot"), ("dsh", "dsh")]:
-            assert rel_l2(ours["grads"][a].cpu().numpy(), g[b]) <= 2e-3, (name, a)
+            assert rel_l2(ours["grads"][a].cpu().numpy(), g[b]) <= 2e-4, (name, a)
         f.close()
 
 
@@ -184,6 +184,87 @@ def test_mark_visible_and_apply_weights_match_reference():
     torch.cuda.synchronize()
     assert torch.equal(c1, c2)
     assert torch.equal(w1, w2)  # mask values are 0/1 -> sums are exact integers in fp32
+
+
+@pytest.mark.parametrize("CH,binary", [(1, False), (2, True), (2, False), (3, True), (3, False)])
+def test_apply_weights_channels_and_float_masks(CH, binary):
+    """apply_weights for CH = 1..3 (cuda_rasterizer/apply_weights.cu:365-380) and non-binary masks: `cnt` advances by
+    CH per (pixel, splat) hit (:331-334) and must be EXACT; `weights` are float sums in a different order than the
+    reference's per-hit atomics: exact for 0/1 masks (integer sums), <= 1e-5 relative for float masks."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    from gaussianeditor_b200.rasterizer import GaussianRasterizer
+    dev = "cuda"
+    cloud, _ = synth.make_config("c3", P=25_000)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 333, 201, 61.0)[CH]      # partial last tile row and column
+    H, W = cam.image_height, cam.image_width
+    ct = cloud_tensors(cloud, dev)
+    rs = settings_from(cam, (0, 0, 0), 0, dev)
+    P = ct["means3D"].shape[0]
+    rng = np.random.default_rng(17 + CH)
+    m = rng.uniform(size=(CH, H, W)).astype(np.float32)
+    if binary:
+        m = (m > 0.4).astype(np.float32)
+    mask = torch.from_numpy(m).to(dev)
+    w1 = torch.zeros(P, CH, device=dev); c1 = torch.zeros(P, 1, dtype=torch.int32, device=dev)
+    w2 = torch.zeros(P, CH, device=dev); c2 = torch.zeros(P, 1, dtype=torch.int32, device=dev)
+    GaussianRasterizer(rs).apply_weights(ct["means3D"], None, ct["opacities"], None, w1, ct["scales"], ct["rotations"],
+                                         None, c1, mask)
+    ref_cuda.ReferenceRasterizer().apply_weights(
+        means3D=ct["means3D"], opacities=ct["opacities"], scales=ct["scales"], rotations=ct["rotations"], weights=w2,
+        cnt=c2, image_weights=mask, bg=rs.bg, viewmatrix=rs.viewmatrix, projmatrix=rs.projmatrix, campos=rs.campos,
+        tanfovx=rs.tanfovx, tanfovy=rs.tanfovy, image_height=H, image_width=W)
+    torch.cuda.synchronize()
+    assert int(c2.sum()) > 0 and int(c2.sum()) % CH == 0
+    assert torch.equal(c1, c2)
+    if binary:
+        assert torch.equal(w1, w2)
+    else:
+        assert rel_l2(w1.cpu().numpy(), w2.cpu().numpy()) <= 1e-5
+        assert float((w1 - w2).abs().max()) <= 1e-4 * float(w2.abs().max())
+    # a second call ACCUMULATES (the reference never zeroes weights / cnt: rasterize_points.cu:223-231)
+    GaussianRasterizer(rs).apply_weights(ct["means3D"], None, ct["opacities"], None, w1, ct["scales"], ct["rotations"],
+                                         None, c1, mask)
+    assert torch.equal(c1, 2 * c2)
+
+
+def test_alpha_output_matches_reference_accum_alpha_and_is_differentiable():
+    """Opt-in alpha image (north star: RGB / depth / alpha): alpha = 1 - final_T must equal 1 - the reference's
+    ImageState::accum_alpha bit for bit; its gradient is checked through the identity
+        color_0 with bg = (-1, 0, 0)  ==  C_0 - T_final  ==  C_0 + alpha - 1,
+    i.e. d/dtheta [ sum G*(color_0 | bg=0) + sum G*alpha ] == d/dtheta sum G*(color_0 | bg=(-1,0,0))."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    from gaussianeditor_b200.rasterizer import GaussianRasterizer
+    dev = "cuda"
+    cloud, _ = synth.make_config("c3", P=40_000)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 333, 201, 61.0)[2]
+    H, W = cam.image_height, cam.image_width
+    G = torch.from_numpy(np.random.default_rng(23).uniform(size=(H, W)).astype(np.float32)).to(dev)
+
+    def run(bg, with_alpha):
+        ct = cloud_tensors(cloud, dev, requires_grad=True)
+        m2 = torch.zeros_like(ct["means3D"], requires_grad=True)
+        rs = settings_from(cam, bg, cloud.sh_degree, dev)
+        out = GaussianRasterizer(rs, return_alpha=with_alpha)(means3D=ct["means3D"], means2D=m2, opacities=ct["opacities"],
+                                                              shs=ct["shs"], scales=ct["scales"], rotations=ct["rotations"])
+        loss = (out[0][0] * G).sum()
+        if with_alpha:
+            assert len(out) == 4 and out[3].shape == (1, H, W)
+            loss = loss + (out[3][0] * G).sum()
+        loss.backward()
+        grads = {k: v.grad.detach().cpu().numpy() for k, v in ct.items()}
+        grads["means2D"] = m2.grad.detach().cpu().numpy()
+        return out, grads
+
+    out_a, g_a = run((0.0, 0.0, 0.0), True)
+    ref = _ref_run(cloud, cam, (0.0, 0.0, 0.0))
+    assert torch.equal(out_a[3][0].detach(), 1.0 - ref["state"]["final_T"])
+    assert torch.equal(out_a[0].detach(), ref["color"])
+    out_b, g_b = run((-1.0, 0.0, 0.0), False)
+    assert len(out_b) == 3
+    for k in g_a:
+        assert rel_l2(g_a[k], g_b[k]) <= 2e-5, (k, rel_l2(g_a[k], g_b[k]))
 
 
 def test_full_size_properties_config3():
@@ -419,6 +500,9 @@ def test_full_size_configs_match_reference_cuda(cfg):
         noise = rel_l2(ref2["grads"][b].cpu().numpy(), r)
         ours_err, ref_err = rel_l2(g, t), rel_l2(r, t)
         assert ours_err <= 5e-5, (cfg, a, ours_err)
+        # the reference's own distance from the truth must stay inside the band observed on B200 (<= 6.3e-4 at
+        # config 3, profiles/README.md), so that a regression of OURS cannot hide behind a growing ref_err term
+        assert ref_err <= 1.5e-3, (cfg, a, ref_err)
         assert rel_l2(g, r) <= 1e-4 + 10 * noise + 1.5 * ref_err, (cfg, a, rel_l2(g, r), noise, ref_err)
 
 
