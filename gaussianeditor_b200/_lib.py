@@ -26,6 +26,8 @@ SYMBOLS = [
     "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close", "gsr_peer_free", "gsr_shard_preprocess_p2p",
     "gsr_forward_preprocess_raw", "gsr_backward_raw",
     "gsr_alpha_image", "gsr_backward_alpha",
+    "gsr_sparse_local_bytes", "gsr_sparse_candidate_bytes", "gsr_sparse_view", "gsr_sparse_preprocess", "gsr_sparse_order",
+    "gsr_sparse_return", "gsr_sparse_backward_preprocess", "gsr_frame_broadcast",
 ]
 
 
@@ -84,6 +86,14 @@ class TileOwner(C.Structure):
 
 class ExchangeView(C.Structure):
     _fields_ = [("records", C.c_void_p)]
+
+
+class SparsePlan(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("slice_len", C.c_int32), ("seg_cap", C.c_int32)]
+
+
+class SparseView(C.Structure):
+    _fields_ = [("records", C.c_void_p), ("ret", C.c_void_p), ("geometry_bytes", C.c_size_t)]
 
 
 _lib = None
@@ -170,6 +180,20 @@ def load():
     lib.gsr_backward_raw.restype = C.c_int
     lib.gsr_backward_raw.argtypes = [S, C.POINTER(RawCloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, sz,
                                      C.POINTER(RawGrads), vp]
+    SP = C.POINTER(SparsePlan)
+    lib.gsr_sparse_local_bytes.restype = sz; lib.gsr_sparse_local_bytes.argtypes = [i32]
+    lib.gsr_sparse_candidate_bytes.restype = sz; lib.gsr_sparse_candidate_bytes.argtypes = [i32, i32]
+    lib.gsr_sparse_view.restype = C.c_int; lib.gsr_sparse_view.argtypes = [vp, i32, i32, C.POINTER(SparseView)]
+    lib.gsr_sparse_preprocess.restype = C.c_int
+    lib.gsr_sparse_preprocess.argtypes = [S, Cl, SP, vp, sz, vp, C.POINTER(vp), sz, vp, vp]
+    lib.gsr_sparse_order.restype = C.c_int
+    lib.gsr_sparse_order.argtypes = [S, SP, vp, sz, vp, vp, vp, vp]
+    lib.gsr_sparse_return.restype = C.c_int
+    lib.gsr_sparse_return.argtypes = [SP, vp, vp, C.POINTER(vp), vp]
+    lib.gsr_sparse_backward_preprocess.restype = C.c_int
+    lib.gsr_sparse_backward_preprocess.argtypes = [S, Cl, SP, vp, sz, vp, vp, sz, vp, sz, C.POINTER(Grads), vp]
+    lib.gsr_frame_broadcast.restype = C.c_int
+    lib.gsr_frame_broadcast.argtypes = [TO, i32, i32, vp, C.POINTER(vp), vp]
     if lib.gsr_abi_version() != 2:
         raise RuntimeError("libgsr_b200.so ABI version mismatch")
     _lib = lib

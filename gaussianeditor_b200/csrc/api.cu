@@ -55,7 +55,7 @@ StageScope::~StageScope() {
   g_prof.push_back(r);
 }
 
-static int validate(const gsr_settings* s, const gsr_cloud* c) {
+int validate_cloud(const gsr_settings* s, const gsr_cloud* c) {
   if (!s || !c) { set_error("null settings/cloud"); return GSR_ERR_INVALID; }
   if (c->P < 0 || s->image_width < 0 || s->image_height < 0) { set_error("negative size"); return GSR_ERR_INVALID; }
   if (c->P == 0) return GSR_OK;  // nothing to read; rasterize_points.cu:72,130 short-circuit the same way
@@ -108,9 +108,32 @@ size_t gsr_binning_bytes(int32_t P, int64_t R, int32_t W, int32_t H) {
 }
 size_t gsr_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * ACC_STRIDE * sizeof(float)); }
 
+// First forward half on a carved workspace: preprocess, depth order, tile-count scan, and the copy of num_rendered to
+// the host. With the tile-binning path (tile_binning.cu) the preprocess kernel accumulates the count itself, so the copy
+// is issued right behind it and the host learns R while the GPU is still sorting.
+static int first_half(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
+                      int32_t* num_rendered_host, cudaStream_t st, bool raw, const float* features_rest) {
+  const int gx = (s.image_width + TILE - 1) / TILE, gy = (s.image_height + TILE - 1) / TILE;
+  const bool v2 = tile_binning_supported(gx, gy);
+  int rc;
+  {
+    StageScope t(ST_PRE_FWD, st);
+    if (v2 && (rc = clear_tile_counts(g, gx, gy, st))) return rc;
+    rc = launch_preprocess_fwd(s, c, g, radii, st, nullptr, 0, raw, features_rest, v2);
+    if (rc) return rc;
+    if (v2) {
+      if ((rc = launch_tile_count(g, gx, gy, TileOwner(), st))) return rc;
+      cudaError_t e = cudaMemcpyAsync(num_rendered_host, g.R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return check_cuda(e, "num_rendered readback");
+    }
+  }
+  StageScope t(ST_DEPTH_SCAN, st);
+  return run_depth_order_and_scan(c, g, v2 ? nullptr : num_rendered_host, st, s.debug != 0);
+}
+
 int gsr_forward_preprocess(const gsr_settings* s, const gsr_cloud* c, void* geometry, size_t geometry_bytes,
                            int32_t* radii, int32_t* num_rendered_host, void* stream) {
-  int rc = validate(s, c);
+  int rc = validate_cloud(s, c);
   if (rc) return rc;
   if (!num_rendered_host) { set_error("num_rendered_host is null"); return GSR_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -119,13 +142,7 @@ int gsr_forward_preprocess(const gsr_settings* s, const gsr_cloud* c, void* geom
   GeometryWS g;
   if (!carve_geometry(geometry, c->P, g)) return GSR_ERR_CUDA;
   if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
-  {
-    StageScope t(ST_PRE_FWD, st);
-    rc = launch_preprocess_fwd(*s, *c, g, radii, st);
-  }
-  if (rc) return rc;
-  StageScope t(ST_DEPTH_SCAN, st);
-  return run_depth_order_and_scan(*c, g, num_rendered_host, st, s->debug != 0);
+  return first_half(*s, *c, g, radii, num_rendered_host, st, false, nullptr);
 }
 
 static int carve_all(const gsr_settings* s, const gsr_cloud* c, int64_t R, void* geometry, size_t gb, void* binning,
@@ -143,7 +160,7 @@ static int forward_render_impl(const gsr_settings* s, const gsr_cloud* c, int32_
                                size_t geometry_bytes, void* binning, size_t binning_bytes, void* image,
                                size_t image_bytes, const int32_t* radii, float* out_color, float* out_depth,
                                void* stream) {
-  int rc = validate(s, c);
+  int rc = validate_cloud(s, c);
   if (rc) return rc;
   if (!out_color || !out_depth) { set_error("output images are null"); return GSR_ERR_INVALID; }
   cudaStream_t st = (cudaStream_t)stream;
@@ -182,7 +199,7 @@ static int backward_impl(const gsr_settings* s, const gsr_cloud* c, int32_t R, c
                          const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
                          const int32_t* radii, const float* dL_dout_color, const float* dL_dout_alpha, void* scratch,
                          size_t scratch_bytes, const gsr_grads* gr, void* stream) {
-  int rc = validate(s, c);
+  int rc = validate_cloud(s, c);
   if (rc) return rc;
   if (!gr || !dL_dout_color) { set_error("grads / dL_dout_color is null"); return GSR_ERR_INVALID; }
   if (c->P == 0) return GSR_OK;
@@ -249,7 +266,7 @@ int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, c
 int gsr_apply_weights(const gsr_settings* s, const gsr_cloud* c, int32_t R, void* geometry, size_t geometry_bytes,
                       void* binning, size_t binning_bytes, void* image, size_t image_bytes, const int32_t* radii,
                       const float* image_weights, int32_t CH, float* weights, int32_t* cnt, void* stream) {
-  int rc = validate(s, c);
+  int rc = validate_cloud(s, c);
   if (rc) return rc;
   if (!image_weights || !weights || !cnt) { set_error("apply_weights: null buffer"); return GSR_ERR_INVALID; }
   if (c->P == 0 || R <= 0) return GSR_OK;
@@ -269,7 +286,7 @@ static int raw_to_cloud(const gsr_settings* s, const gsr_raw_cloud* r, gsr_cloud
   c = gsr_cloud{};
   c.P = r->P; c.means3D = r->means3D; c.opacities = r->opacity_logits; c.shs = r->features_dc;
   c.scales = r->log_scales; c.rotations = r->raw_rotations;
-  int rc = validate(s, &c);
+  int rc = validate_cloud(s, &c);
   if (rc) return rc;
   if (r->P > 0 && s->sh_coeffs > 1 && !r->features_rest) { set_error("features_rest is null but sh_coeffs = %d", s->sh_coeffs); return GSR_ERR_INVALID; }
   if (r->features_rest && (reinterpret_cast<uintptr_t>(r->features_rest) & 15)) { set_error("features_rest must be 16-byte aligned"); return GSR_ERR_INVALID; }
@@ -288,13 +305,7 @@ int gsr_forward_preprocess_raw(const gsr_settings* s, const gsr_raw_cloud* r, vo
   GeometryWS g;
   if (!carve_geometry(geometry, c.P, g)) return GSR_ERR_CUDA;
   if (g.total > geometry_bytes) { set_error("geometry workspace too small: %zu < %zu", geometry_bytes, g.total); return GSR_ERR_WORKSPACE; }
-  {
-    StageScope t(ST_PRE_FWD, st);
-    rc = launch_preprocess_fwd(*s, c, g, radii, st, nullptr, 0, true, r->features_rest);
-  }
-  if (rc) return rc;
-  StageScope t(ST_DEPTH_SCAN, st);
-  return run_depth_order_and_scan(c, g, num_rendered_host, st, s->debug != 0);
+  return first_half(*s, c, g, radii, num_rendered_host, st, true, r->features_rest);
 }
 
 int gsr_backward_raw(const gsr_settings* s, const gsr_raw_cloud* r, int32_t R, const void* geometry,
@@ -370,7 +381,7 @@ int gsr_view_exchange(void* geometry, int32_t P_total, gsr_exchange_view* out) {
 
 int gsr_shard_preprocess(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
                          int32_t slice_len, void* geometry, size_t geometry_bytes, int32_t* radii_total, void* stream) {
-  int rc = validate(s, shard);
+  int rc = validate_cloud(s, shard);
   if (rc) return rc;
   if (P_total <= 0 || index_base < 0 || slice_len < shard->P || (int64_t)index_base + slice_len > P_total) {
     set_error("shard [%d, %d+%d) (P=%d) does not fit P_total=%d", index_base, index_base, slice_len, shard->P, P_total);
@@ -424,7 +435,7 @@ int gsr_peer_free(void* ptr) { return ptr ? check_cuda(cudaFree(ptr), "peer_free
 int gsr_shard_preprocess_p2p(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
                              int32_t slice_len, void* const* peer_geometry, int32_t world, int32_t rank,
                              size_t geometry_bytes, int32_t* radii_total, void* stream) {
-  int rc = validate(s, shard);
+  int rc = validate_cloud(s, shard);
   if (rc) return rc;
   if (world < 1 || world > GSR_MAX_PEERS || rank < 0 || rank >= world || !peer_geometry) {
     set_error("p2p preprocess: need 1 <= world <= %d, 0 <= rank < world", GSR_MAX_PEERS);
@@ -475,7 +486,13 @@ int gsr_shard_order(const gsr_settings* s, const gsr_tile_owner* owner, int32_t 
   if (rc) return rc;
   gsr_cloud c{};
   c.P = P_total;
-  return run_depth_order_and_scan(c, g, num_rendered_host, st, s->debug != 0);
+  const bool v2 = tile_binning_supported((s->image_width + TILE - 1) / TILE, (s->image_height + TILE - 1) / TILE);
+  if (v2) {
+    if ((rc = launch_tile_count(g, (s->image_width + TILE - 1) / TILE, (s->image_height + TILE - 1) / TILE, own, st))) return rc;
+    cudaError_t e = cudaMemcpyAsync(num_rendered_host, g.R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return check_cuda(e, "num_rendered readback");
+  }
+  return run_depth_order_and_scan(c, g, v2 ? nullptr : num_rendered_host, st, s->debug != 0);
 }
 
 int gsr_shard_render(const gsr_settings* s, const gsr_tile_owner* owner, int32_t P_total, int32_t R, void* geometry,
@@ -528,7 +545,7 @@ int gsr_shard_backward_render(const gsr_settings* s, const gsr_tile_owner* owner
 int gsr_shard_backward_preprocess(const gsr_settings* s, const gsr_cloud* shard, int32_t P_total, int32_t index_base,
                                   const void* geometry, size_t geometry_bytes, const int32_t* radii_total,
                                   const void* acc_slice, const gsr_grads* gr, void* stream) {
-  int rc = validate(s, shard);
+  int rc = validate_cloud(s, shard);
   if (rc) return rc;
   if (P_total <= 0 || index_base < 0 || (int64_t)index_base + shard->P > P_total) { set_error("shard does not fit P_total"); return GSR_ERR_INVALID; }
   if (shard->P == 0) return GSR_OK;
@@ -578,6 +595,7 @@ int gsr_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "preprocess_variant")) g_opt.preprocess_variant = (int)value;
   else if (!strcmp(name, "profile")) g_opt.profile = (int)value;
   else if (!strcmp(name, "tile_key_bits")) g_opt.tile_key_bits = (int)value;
+  else if (!strcmp(name, "binning_variant")) g_opt.binning_variant = (int)value;
   else if (!strcmp(name, "stats")) {
     if (value && !g_stats_dev) {
       if (cudaMalloc((void**)&g_stats_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) return check_cuda(cudaGetLastError(), "stats alloc");
@@ -606,6 +624,7 @@ int64_t gsr_get_option(const char* name) {
   if (!strcmp(name, "preprocess_variant")) return g_opt.preprocess_variant;
   if (!strcmp(name, "profile")) return g_opt.profile;
   if (!strcmp(name, "tile_key_bits")) return g_opt.tile_key_bits;
+  if (!strcmp(name, "binning_variant")) return g_opt.binning_variant;
   return -1;
 }
 int64_t gsr_launch_count(void) { return g_launches; }

@@ -54,6 +54,15 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
   rmax.y = (unsigned)min(gy, max((int)0, (int)((py + radius + TILE - 1) / TILE)));
 }
 
+// the four corners of a tile rectangle in the (gy+1) x (gx+1) difference array (tile_binning.cu: tile_prefix_kernel)
+__device__ __forceinline__ void add_tile_rect(int32_t* diff, int gx, uint2 rmin, uint2 rmax) {
+  const int stride = gx + 1;
+  atomicAdd(diff + rmin.y * stride + rmin.x, 1);
+  atomicAdd(diff + rmin.y * stride + rmax.x, -1);
+  atomicAdd(diff + rmax.y * stride + rmin.x, -1);
+  atomicAdd(diff + rmax.y * stride + rmax.x, 1);
+}
+
 // Rows of the rectangle [rmin.y, rmax.y) this rank owns (ty % stride == phase): first owned row and their number.
 __device__ __forceinline__ void owned_rows(uint32_t ymin, uint32_t ymax, int stride, int phase, uint32_t& y0, uint32_t& ny) {
   if (stride == 1) { y0 = ymin; ny = ymax - ymin; return; }
@@ -71,25 +80,31 @@ __device__ __forceinline__ void owned_rows(uint32_t ymin, uint32_t ymax, int str
 // emits nothing.
 __global__ void retouch_kernel(int P, const SplatRecord* __restrict__ records, int gx, int gy, int stride, int phase,
                                int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
-                               uint32_t* __restrict__ ident, uint32_t* __restrict__ depth_keys) {
+                               uint32_t* __restrict__ ident, uint32_t* __restrict__ depth_keys,
+                               int32_t* __restrict__ tile_diff) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= P) return;
-  const float4* r = reinterpret_cast<const float4*>(records + idx);
-  const int radius = __float_as_int(__ldg(r + 2).w);
-  uint32_t n = 0, key = 0xFFFFFFFFu;
-  if (radius > 0) {
-    const float4 q0 = __ldg(r);
-    uint2 rmin, rmax;
-    tile_rect(q0.x, q0.y, radius, gx, gy, rmin, rmax);
-    uint32_t y0, ny;
-    owned_rows(rmin.y, rmax.y, stride, phase, y0, ny);
-    n = ny * (rmax.x - rmin.x);
-    if (n != 0) key = __float_as_uint(__ldg(r + 1).z);
+  uint32_t n = 0;
+  if (idx < P) {
+    const float4* r = reinterpret_cast<const float4*>(records + idx);
+    const int radius = __float_as_int(__ldg(r + 2).w);
+    uint32_t key = 0xFFFFFFFFu;
+    if (radius > 0) {
+      const float4 q0 = __ldg(r);
+      uint2 rmin, rmax;
+      tile_rect(q0.x, q0.y, radius, gx, gy, rmin, rmax);
+      uint32_t y0, ny;
+      owned_rows(rmin.y, rmax.y, stride, phase, y0, ny);
+      n = ny * (rmax.x - rmin.x);
+      if (n != 0) {
+        key = __float_as_uint(__ldg(r + 1).z);
+        if (tile_diff) add_tile_rect(tile_diff, gx, rmin, rmax);  // full rectangle: tile_prefix_kernel keeps the owned rows
+      }
+    }
+    radii[idx] = radius;
+    tiles_touched[idx] = n;
+    ident[idx] = (uint32_t)idx;
+    depth_keys[idx] = key;
   }
-  radii[idx] = radius;
-  tiles_touched[idx] = n;
-  ident[idx] = (uint32_t)idx;
-  depth_keys[idx] = key;
 }
 
 // One thread per OUTPUT slot (instance): perfectly balanced no matter how the tile counts are distributed --
@@ -309,6 +324,8 @@ bool carve_geometry(void* base, int P, GeometryWS& ws) {
   ws.depth_keys_sorted = (uint32_t*)take(n * 4);
   ws.depth_order = (uint32_t*)take(n * 4);
   ws.offsets = (uint32_t*)take(n * 4);
+  ws.R_dev = (uint32_t*)take(16 + (size_t)MAX_TILE_DIFF * sizeof(int32_t));  // one block: R, then the array
+  ws.tile_diff = reinterpret_cast<int32_t*>(ws.R_dev + 4);
   size_t t1 = depth_sort_temp_bytes((int)n), t2 = scan_temp_bytes((int)n);
   if (cudaPeekAtLastError() != cudaSuccess) {
     check_cuda(cudaGetLastError(), "CUB temp-size query");
@@ -321,7 +338,7 @@ bool carve_geometry(void* base, int P, GeometryWS& ws) {
 }
 
 bool carve_binning(void* base, int P, int64_t R, int W, int H, BinningWS& ws) {
-  (void)P; (void)W; (void)H;
+  (void)P;
   size_t off = 0;
   char* b = (char*)base;
   auto take = [&](size_t bytes) {
@@ -340,6 +357,11 @@ bool carve_binning(void* base, int P, int64_t R, int W, int H, BinningWS& ws) {
     return false;
   }
   ws.cub_temp = take(ws.cub_temp_bytes);
+  // tile_binning.cu: tickets + digit bases (1024 words), two passes of per-sort-tile status words, 2-D count scratch
+  const size_t gx = (size_t)(W + TILE - 1) / TILE, gy = (size_t)(H + TILE - 1) / TILE;
+  const size_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+  ws.sort_state_bytes = (1024 + 2 * ntiles * 256 + (gx + 1) * (gy + 1)) * sizeof(uint32_t);
+  ws.sort_state = (uint32_t*)take(ws.sort_state_bytes);
   ws.total = off;
   return true;
 }
@@ -363,6 +385,7 @@ void carve_image(void* base, int W, int H, ImageWS& ws) {
 
 int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
                              bool debug) {
+  // num_rendered_host == nullptr: the caller already fetched the count from g.R_dev (tile_binning path)
   const int P = c.P;
   size_t tb = g.cub_temp_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, (const uint32_t*)g.depth_keys, g.depth_keys_sorted,
@@ -375,8 +398,10 @@ int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* n
   e = cub::DeviceScan::InclusiveSum(g.cub_temp, tb, it, g.offsets, P, st);
   g_launches += 2;
   if (e != cudaSuccess) return check_cuda(e, "tile-count scan");
-  e = cudaMemcpyAsync(num_rendered_host, g.offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-  if (e != cudaSuccess) return check_cuda(e, "num_rendered readback");
+  if (num_rendered_host) {
+    e = cudaMemcpyAsync(num_rendered_host, g.offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return check_cuda(e, "num_rendered readback");
+  }
   return check_launch("depth order + scan", debug, st);
 }
 
@@ -385,6 +410,7 @@ int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculati
   const int W = s.image_width, H = s.image_height;
   const int gx = (W + TILE - 1) / TILE, gy = (H + TILE - 1) / TILE;
   const bool debug = s.debug != 0;
+  if (R > 0 && R < (1 << 30) && tile_binning_supported(gx, gy)) return run_tile_binning(s, c.P, R, speculative, g, b, im, radii, st, own);
   cudaError_t e = cudaMemsetAsync(im.ranges, 0, (size_t)gx * gy * sizeof(uint2), st);
   if (e != cudaSuccess) return check_cuda(e, "ranges memset");
   if (R <= 0) return GSR_OK;
@@ -397,8 +423,13 @@ int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculati
 int launch_retouch(const gsr_settings& s, int P, const GeometryWS& g, int32_t* radii, const TileOwner& own,
                    cudaStream_t st) {
   const int gx = (s.image_width + TILE - 1) / TILE, gy = (s.image_height + TILE - 1) / TILE;
+  const bool v2 = tile_binning_supported(gx, gy);
+  if (v2) {
+    int rc = clear_tile_counts(g, gx, gy, st);
+    if (rc) return rc;
+  }
   retouch_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, g.records, gx, gy, own.stride, own.phase, radii, g.tiles_touched,
-                                                  g.ident, g.depth_keys);
+                                                  g.ident, g.depth_keys, v2 ? g.tile_diff : nullptr);
   g_launches++;
   return check_launch("retouch", s.debug != 0, st);
 }

@@ -35,10 +35,15 @@ struct GeometryWS {
   uint32_t* depth_keys_sorted;
   uint32_t* depth_order;    // [P] Gaussian indices in (depth, index) order
   uint32_t* offsets;        // [P] inclusive scan of tiles_touched in depth order
+  uint32_t* R_dev;          // [4]  word 0: number of instances (tile_binning.cu: tile_count_kernel)
+  int32_t* tile_diff;       // [MAX_TILE_DIFF] 2-D difference array of the tile rectangles, (gy+1) x (gx+1), directly
+                            //      behind R_dev so that one memset clears both
   void* cub_temp;
   size_t cub_temp_bytes;
   size_t total;
 };
+// (gx+1)*(gy+1) <= 2*65536 + 1 for every grid with gx*gy < 65536 tiles (the limit of the 16-bit tile keys)
+constexpr int MAX_TILE_DIFF = 2 * 65536 + 64;
 struct BinningWS {
   uint32_t* keys_unsorted;  // [R] tile id
   uint32_t* keys_sorted;    // [R]
@@ -46,6 +51,10 @@ struct BinningWS {
   uint32_t* point_list;     // [R] sorted
   void* cub_temp;
   size_t cub_temp_bytes;
+  // tile_binning.cu (own radix passes with decoupled look-back): per pass and sort tile one status word per digit,
+  // plus [0..1] ticket counters and [2 .. 2+512) the exclusive digit bases of both passes
+  uint32_t* sort_state;
+  size_t sort_state_bytes;
   size_t total;
 };
 struct ImageWS {
@@ -79,6 +88,7 @@ struct Options {
   int preprocess_variant = 1;
   int profile = 0;
   int tile_key_bits = 16;
+  int binning_variant = 1;     // 0 = emit kernel + CUB tile sort + tile_ranges, 1 = tile_binning.cu
 };
 enum Stage { ST_PRE_FWD = 0, ST_DEPTH_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_RENDER_FWD, ST_RENDER_BWD, ST_PRE_BWD, ST_APPLY_W };
 // RAII stage timer: records two events on `st` when profiling is on, otherwise free.
@@ -95,6 +105,7 @@ extern std::atomic<long long> g_launches;
 void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int check_launch(const char* what, bool debug, cudaStream_t st);
+int validate_cloud(const gsr_settings* s, const gsr_cloud* c);  // argument checks of the reference's Python/C++ glue
 
 // ---- stage entry points (host side; each file owns its kernels) ------------------------------------------
 // peer_records/npeers: fused all-gather of the sharded path (every rank's view of this shard's record slice), else 0
@@ -102,7 +113,7 @@ int check_launch(const char* what, bool debug, cudaStream_t st);
 // c.shs is features_dc [P,1,3] and features_rest [P,M-1,3] holds the other coefficients (may be null when M == 1).
 int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
                           cudaStream_t st, SplatRecord* const* peer_records = nullptr, int npeers = 0, bool raw = false,
-                          const float* features_rest = nullptr);
+                          const float* features_rest = nullptr, bool count_tiles = false);
 int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
                              bool debug);
 // Sharded path: recompute tiles_touched (owned tile rows only) and the sort identity for all P gathered Gaussians.
@@ -111,6 +122,15 @@ int launch_retouch(const gsr_settings& s, int P, const GeometryWS& g, int32_t* r
 int run_binning(const gsr_settings& s, const gsr_cloud& c, int R, bool speculative, const GeometryWS& g,
                 const BinningWS& b, const ImageWS& im, const int32_t* radii, cudaStream_t st,
                 const TileOwner& own = TileOwner());
+// tile_binning.cu: ranges from the tile-count difference array, emission fused into the first of two own radix passes
+constexpr int SORT_TILE = 4096;  // instances per CTA of a radix pass
+bool tile_binning_supported(int gx, int gy);
+int run_tile_binning(const gsr_settings& s, int P, int R, bool speculative, const GeometryWS& g, const BinningWS& b,
+                     const ImageWS& im, const int32_t* radii, cudaStream_t st, const TileOwner& own);
+// clears R_dev + the difference array of a gx x gy grid (before the kernel that accumulates them)
+int clear_tile_counts(const GeometryWS& g, int gx, int gy, cudaStream_t st);
+// g.R_dev[0] = number of instances in the owned tile rows = a weighted sum over the difference array (no prefix needed)
+int launch_tile_count(const GeometryWS& g, int gx, int gy, const TileOwner& own, cudaStream_t st);
 int launch_render_fwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,
                       float* out_color, float* out_depth, cudaStream_t st, const TileOwner& own = TileOwner());
 int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningWS& b, const ImageWS& im,

@@ -57,6 +57,11 @@ struct PreArgs {
   // TMA bulk store per destination into the records array of every rank (own copy included) over NVLink peer memory.
   SplatRecord* peer_records[GSR_MAX_PEERS];  // pointers to THIS shard's slice inside each rank's records array
   int npeers;
+  // Tile binning without a pass over the instances (tile_binning.cu): every visible Gaussian adds the four corners of
+  // its tile rectangle to a 2-D difference array (its 2-D prefix sum is the per-tile instance count -> tile ranges and
+  // the radix histograms, its weighted sum is R). Null in the sharded paths (the tile owner does it).
+  int32_t* tile_diff;
+  int vec_ok;  // means3D and scales are 16-byte aligned: full blocks use 128-bit cooperative loads
 };
 
 // SH basis weights of forward.cu:30-61 for the unit view direction (x,y,z), pinned to the operation sequence nvcc emits
@@ -122,8 +127,30 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
   __shared__ __align__(128) float s_rest[RAW ? PRE_THREADS * 45 : 1];
   __shared__ uint64_t bar;
 
+  // the CTA's means and scales (128 x 12 B each, contiguous in HBM) arrive through 96 coalesced 128-bit loads per
+  // array instead of three stride-3 scalar loads per thread; the word stride 3 is coprime with the 32 banks
+  __shared__ __align__(16) float s_mean[PRE_THREADS * 3];
+  __shared__ __align__(16) float s_scale[PRE_THREADS * 3];
+
   const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
   const bool live = idx < a.P;
+  {
+    const int first = blockIdx.x * PRE_THREADS;
+    const int nhere = min(PRE_THREADS, a.P - first);
+    const bool has_scale = a.cov3D_precomp == nullptr;
+    if (nhere == PRE_THREADS && a.vec_ok) {
+      if (threadIdx.x < 96)
+        reinterpret_cast<float4*>(s_mean)[threadIdx.x] = __ldg(reinterpret_cast<const float4*>(a.means3D + (size_t)3 * first) + threadIdx.x);
+      if (has_scale && threadIdx.x >= 32)
+        reinterpret_cast<float4*>(s_scale)[threadIdx.x - 32] = __ldg(reinterpret_cast<const float4*>(a.scales + (size_t)3 * first) + (threadIdx.x - 32));
+    } else {
+      for (int i = threadIdx.x; i < 3 * nhere; i += PRE_THREADS) {
+        s_mean[i] = a.means3D[(size_t)3 * first + i];
+        if (has_scale) s_scale[i] = a.scales[(size_t)3 * first + i];
+      }
+    }
+  }
+  if (!(BULK_SH || RAW)) __syncthreads();  // the other variants synchronise right below (mbarrier init)
 
   if (BULK_SH || RAW) {
     if (threadIdx.x == 0) {
@@ -138,7 +165,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
   float3 p_view = make_float3(0.f, 0.f, 0.f);
   bool vis = false;
   if (live) {
-    p_orig = make_float3(a.means3D[3 * idx], a.means3D[3 * idx + 1], a.means3D[3 * idx + 2]);
+    p_orig = make_float3(s_mean[3 * threadIdx.x], s_mean[3 * threadIdx.x + 1], s_mean[3 * threadIdx.x + 2]);
     const float* m = a.view;  // transformPoint4x3 (auxiliary.h:58-66), contraction pinned like the rest
     p_view.x = __fadd_rn(__fmaf_rn(m[8], p_orig.z, __fmaf_rn(m[0], p_orig.x, __fmul_rn(m[4], p_orig.y))), m[12]);
     p_view.y = __fadd_rn(__fmaf_rn(m[9], p_orig.z, __fmaf_rn(m[1], p_orig.x, __fmul_rn(m[5], p_orig.y))), m[13]);
@@ -158,20 +185,11 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
       bulk_g2s(s_rest, a.features_rest + (size_t)first * K3, bytes, &bar);
     }
   }
-  if (BULK_SH) {
-    // One TMA row fetch per surviving Gaussian; everybody arrives exactly once on the CTA barrier.
-    const uint32_t nbytes = (uint32_t)(((a.D + 1) * (a.D + 1) * 12 + 15) & ~15);
-    if (vis && want_sh) {
-      mbar_arrive_expect_tx(&bar, nbytes);
-      bulk_g2s(&sh_rows[threadIdx.x * SH_ROW_WORDS], a.shs + (size_t)idx * a.M * 3, nbytes, &bar);
-    } else {
-      mbar_arrive(&bar);
-    }
-  }
 
   int my_radius_i = 0;
   uint32_t tiles = 0;
   uint32_t depth_key = 0xFFFFFFFFu;
+  uint2 rect_min = make_uint2(0, 0), rect_max = make_uint2(0, 0);
   SplatRecord rec;
   bool emit = false;
 
@@ -196,7 +214,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
 #pragma unroll
       for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[(size_t)idx * 6 + k];
     } else {
-      float3 scale = make_float3(a.scales[3 * idx], a.scales[3 * idx + 1], a.scales[3 * idx + 2]);
+      float3 scale = make_float3(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1], s_scale[3 * threadIdx.x + 2]);
       float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
       if (RAW) {
         scale = make_float3(expf(scale.x), expf(scale.y), expf(scale.z));
@@ -284,7 +302,6 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
       float my_radius = ceilf(__fmul_rn(3.f, sqrtf(fmaxf(lambda1, lambda2))));
       float2 point_image = make_float2(ndc_to_pix(p_proj.x, a.W), ndc_to_pix(p_proj.y, a.H));
       const int max_radius = (int)my_radius;
-      uint2 rect_min, rect_max;
       rect_min.x = (unsigned)min(a.gx, max((int)0, (int)((point_image.x - max_radius) / TILE)));
       rect_min.y = (unsigned)min(a.gy, max((int)0, (int)((point_image.y - max_radius) / TILE)));
       rect_max.x = (unsigned)min(a.gx, max((int)0, (int)((point_image.x + max_radius + TILE - 1) / TILE)));
@@ -297,6 +314,19 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
         rec.q0 = make_float4(point_image.x, point_image.y, conic.x, conic.y);
         rec.q1 = make_float4(conic.z, RAW ? sigmoid_act(a.opacities[idx]) : a.opacities[idx], p_view.z, 0.f);
       }
+    }
+  }
+
+  if (BULK_SH) {
+    // One TMA row fetch per Gaussian that will emit a record (in front of the near plane AND a non-empty tile
+    // rectangle: the ~20 % that pass the z test but miss the screen never touch their SH bytes); everybody arrives
+    // exactly once on the CTA barrier. The latency of the fetch is covered by the other resident CTAs (8 per SM).
+    const uint32_t nbytes = (uint32_t)(((a.D + 1) * (a.D + 1) * 12 + 15) & ~15);
+    if (emit && want_sh) {
+      mbar_arrive_expect_tx(&bar, nbytes);
+      bulk_g2s(&sh_rows[threadIdx.x * SH_ROW_WORDS], a.shs + (size_t)idx * a.M * 3, nbytes, &bar);
+    } else {
+      mbar_arrive(&bar);
     }
   }
 
@@ -379,6 +409,15 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
       bulk_wait_read0();  // shared memory must stay intact until the TMA unit has read it
     }
   }
+  if (a.tile_diff != nullptr) {
+    if (emit) {
+      const int stride = a.gx + 1;
+      atomicAdd(a.tile_diff + rect_min.y * stride + rect_min.x, 1);
+      atomicAdd(a.tile_diff + rect_min.y * stride + rect_max.x, -1);
+      atomicAdd(a.tile_diff + rect_max.y * stride + rect_min.x, -1);
+      atomicAdd(a.tile_diff + rect_max.y * stride + rect_max.x, 1);
+    }
+  }
   if (live) {
     a.radii[idx] = my_radius_i;
     a.tiles_touched[idx] = tiles;
@@ -401,7 +440,7 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 
 int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
                           cudaStream_t st, SplatRecord* const* peer_records, int npeers, bool raw,
-                          const float* features_rest) {
+                          const float* features_rest, bool count_tiles) {
   PreArgs a;
   a.features_rest = features_rest;
   a.npeers = npeers;
@@ -417,6 +456,8 @@ int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const Geome
   a.view = s.viewmatrix; a.proj = s.projmatrix; a.campos = s.campos;
   a.records = g.records; a.tiles_touched = g.tiles_touched; a.clamped = g.clamped;
   a.depth_keys = g.depth_keys; a.ident = g.ident; a.radii = radii;
+  a.vec_ok = ((reinterpret_cast<uintptr_t>(c.means3D) | reinterpret_cast<uintptr_t>(c.scales)) & 15) == 0;
+  a.tile_diff = count_tiles ? g.tile_diff : nullptr;
   const int grid = (c.P + PRE_THREADS - 1) / PRE_THREADS;
   // TMA row fetch needs 16-byte aligned rows: M*12 % 16 == 0 and an aligned base pointer.
   const bool bulk = g_opt.preprocess_variant >= 1 && c.colors_precomp == nullptr && c.shs != nullptr &&

@@ -15,6 +15,7 @@ Differences a caller can observe (all documented in DESIGN.md):
 from __future__ import annotations
 
 import ctypes as C
+import time
 from typing import NamedTuple
 
 import torch
@@ -81,6 +82,19 @@ def _pinned_i32(device):
     return _pinned[key]
 
 
+def _wait_count(pinned: torch.Tensor, waiter) -> int:
+    """num_rendered arrives in a pinned host word (preset to -1) through an async copy that the library issues right
+    behind the preprocess kernel, i.e. BEFORE the depth sort it has already queued: spinning on the word hands the
+    count to the host while the GPU is still busy, instead of sleeping until the whole first half has drained.
+    Falls back to `waiter()` (event / stream synchronize) after 2 ms."""
+    t0 = time.perf_counter()
+    while int(pinned[0]) < 0:
+        if time.perf_counter() - t0 > 2e-3:
+            waiter()
+            break
+    return int(pinned[0])
+
+
 def _make_settings(rs: GaussianRasterizationSettings, M: int, device, keep: list) -> _lib.Settings:
     bg = _f32c(rs.bg, device); view = _f32c(rs.viewmatrix, device)
     proj = _f32c(rs.projmatrix, device); campos = _f32c(rs.campos, device)
@@ -135,6 +149,7 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
         gbytes = _geometry_bytes(lib, P) if P > 0 else 0
         state.geom = torch.empty(gbytes, **u8)
         pinned = _pinned_i32(device)
+        pinned[0] = -1
         if raw:
             rc = _lib.RawCloud(P, _ptr(means3D), _ptr(opacities), _ptr(sh), _ptr(raw_rest), _ptr(scales), _ptr(rotations))
             _lib.check(lib.gsr_forward_preprocess_raw(C.byref(s), C.byref(rc), _ptr(state.geom), gbytes,
@@ -166,13 +181,11 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
                                                           _ptr(state.binning), bbytes, _ptr(state.img), ibytes,
                                                           _ptr(state.radii), _ptr(color), _ptr(depth), st),
                        "gsr_forward_render_speculative")
-            ev.synchronize()
-            R = int(pinned[0])
+            R = _wait_count(pinned, ev.synchronize)
             if R <= cap:
                 state.num_rendered, state.cap, done = R, cap, True
         if not done:
-            stream.synchronize()
-            R = int(pinned[0])
+            R = _wait_count(pinned, stream.synchronize)
             state.num_rendered = state.cap = R
             bbytes = lib.gsr_binning_bytes(P, R, W, H) if R > 0 else 0
             state.binning = torch.empty(bbytes, **u8)

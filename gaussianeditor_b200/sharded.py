@@ -446,24 +446,70 @@ class _ShardedRasterize(torch.autograd.Function):
         return (*grads, None, None, None, None)
 
 
+def p2p_available(exchange: "Exchange") -> bool:
+    """Peer mappings need every rank of the group on ONE node with peer access between all device pairs. Checked
+    collectively (every rank gets the same answer), so that all ranks take the same code path."""
+    import os
+    if exchange.backend != "nccl" or exchange.world > 8:
+        return False
+    ok = int(os.environ.get("LOCAL_WORLD_SIZE", exchange.world)) == exchange.world
+    try:
+        me = torch.cuda.current_device()
+        n = torch.cuda.device_count()
+        ok = ok and n >= exchange.world and all(torch.cuda.can_device_access_peer(me, d) for d in range(n) if d != me)
+    except Exception:
+        ok = False
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=torch.device("cuda", torch.cuda.current_device()))
+    exchange.dist.all_reduce(flag, op=exchange.dist.ReduceOp.MIN, group=exchange.group)
+    return bool(int(flag[0]))
+
+
 class ShardedGaussianRasterizer(nn.Module):
     """``GaussianRasterizer`` for a cloud sharded by Gaussian index over the ranks of a process group.
 
     ``forward`` takes THIS RANK's rows of the per-Gaussian tensors (``shard_slice(full, plan)``) and returns the
     full image on every rank plus the radii of this rank's Gaussians; gradients flow to the local rows.
+
+    ``mode``: ``"sparse"`` (default when peer mappings are available) -- records, the depth sort and the gradient rows
+    only involve the ranks whose tile rows a Gaussian touches (sparse_sharded.py); ``"dense"`` -- every rank receives,
+    sorts and reduces all P_total records (fused peer-store all-gather with ``p2p=True``, NCCL all-gather otherwise).
+    ``max_in_flight``: forwards whose autograd state may be alive at the same time (GaussianEditor: 2).
     """
 
     def __init__(self, raster_settings: GaussianRasterizationSettings, P_total: int, group=None,
-                 p2p: Optional[bool] = None):
+                 p2p: Optional[bool] = None, mode: Optional[str] = None, max_in_flight: int = 2):
         super().__init__()
         self.raster_settings = raster_settings
         self.exchange = Exchange(group)
         self.plan = ShardPlan(int(P_total), self.exchange.world, self.exchange.rank)
-        # p2p: fused preprocess + all-gather through peer-mapped workspaces (needs NVLink/P2P between all ranks of
-        # one node; measured 2xB200, config 4: 2.15 ms/step vs ~2.33 with the NCCL all-gather). Default on for NCCL.
-        if p2p is None:
-            p2p = self.exchange.backend == "nccl" and self.exchange.world <= 8
-        self.pool = WorkspacePool(self.exchange, _geometry_bytes(_lib.load(), self.plan.P_pad), bool(p2p))
+        can_p2p = p2p_available(self.exchange) if (p2p is None or p2p or mode == "sparse") else False
+        if p2p and not can_p2p:
+            raise RuntimeError("p2p=True needs all ranks on one node with peer access between every device pair")
+        if mode is None:
+            mode = "sparse" if (can_p2p and p2p is not False) else "dense"
+        if mode not in ("sparse", "dense"):
+            raise ValueError("mode must be 'sparse' or 'dense'")
+        if mode == "sparse" and not can_p2p:
+            raise RuntimeError("mode='sparse' needs peer mappings (all ranks on one node with peer access)")
+        self.mode = mode
+        self.pool = self.sparse_pool = None
+        if mode == "sparse":
+            from . import sparse_sharded as SS
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.sparse_pool = SS.SparsePool(self.plan, dev, int(raster_settings.image_width),
+                                             int(raster_settings.image_height), self.exchange, depth=max_in_flight)
+        else:
+            # fused preprocess + all-gather through peer-mapped workspaces (measured 2xB200, config 4: 2.15 ms/step vs
+            # ~2.33 with the NCCL all-gather)
+            self.pool = WorkspacePool(self.exchange, _geometry_bytes(_lib.load(), self.plan.P_pad),
+                                      bool(can_p2p if p2p is None else p2p))
+
+    def close(self):
+        """Release the peer-mapped workspaces (collective: every rank must call it)."""
+        if self.pool is not None:
+            self.pool.close()
+        if self.sparse_pool is not None:
+            self.sparse_pool.close()
 
     def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
                 cov3D_precomp=None):
@@ -478,5 +524,13 @@ class ShardedGaussianRasterizer(nn.Module):
         scales = empty if scales is None else scales
         rotations = empty if rotations is None else rotations
         cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        rs = self.raster_settings
+        if self.mode == "sparse":
+            from . import sparse_sharded as SS
+            rk0 = self.sparse_pool.all[0]
+            if int(rs.image_width) != rk0.W or int(rs.image_height) != rk0.H:
+                raise RuntimeError("sparse mode: the image size is fixed at construction (peer-mapped frames)")
+            return SS._SparseShardedRasterize.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                                    cov3D_precomp, rs, self.sparse_pool, self.exchange)
         return _ShardedRasterize.apply(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                       cov3D_precomp, self.raster_settings, self.plan, self.exchange, self.pool)
+                                       cov3D_precomp, rs, self.plan, self.exchange, self.pool)

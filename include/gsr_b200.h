@@ -285,6 +285,60 @@ GSR_API int gsr_shard_preprocess_p2p(const gsr_settings* s, const gsr_cloud* sha
                              int32_t slice_len, void* const* peer_geometry /* [world] host array */, int32_t world,
                              int32_t rank, size_t geometry_bytes, int32_t* radii_total, void* stream);
 
+/* ---- sparse exchange for the Gaussian-sharded path -------------------------------------------------------------
+ * The dense scheme above moves, sorts and reduces P_total-sized arrays on every rank. Here a splat record travels only
+ * to the ranks whose tile rows (ty % world == d) its tile rectangle touches, into slot  rank*seg_cap + j  of that
+ * rank's CANDIDATE array, where j is the record's position among this rank's Gaussians bound for d, in index order.
+ * The candidate array (world segments of capacity seg_cap; unused slots are holes with the "culled" sort key) is in
+ * global-index order, so the existing stable depth sort / scan / binning / blending stages run on it unchanged as a
+ * cloud of world*seg_cap Gaussians (gsr_shard_render / gsr_shard_backward_render with P_total = world*seg_cap and the
+ * candidate workspace as `geometry`) and produce the single-GPU lists of the owned tiles bit for bit. The backward
+ * returns each candidate's 12-float accumulator row to slot  d*seg_cap + j  of the OWNER's `ret` array, where the
+ * owner adds the <= world partial rows of each Gaussian in ascending rank order (deterministic).
+ *
+ *   forward : gsr_sparse_preprocess   preprocess + destination masks + ordered slots + peer stores of the records;
+ *                                     writes counts_row[d] = n[rank -> d]
+ *             -- host: all-reduce(sum) of the [world, GSR_MAX_PEERS] count matrix (row = source, written by its rank). It is also the barrier that
+ *                orders the peer stores before the readers. --
+ *             gsr_sparse_order        candidates -> radii / owned-tile counts / depth order / scan; host_out[0] =
+ *                                     num_rendered of this rank, host_out[1] = max over the matrix (a value > seg_cap
+ *                                     means some segment overflowed on some rank: redo the step with a larger seg_cap)
+ *             gsr_shard_render        (existing)   -> gsr_frame_broadcast or an all-reduce of the frames
+ *   backward: gsr_shard_backward_render (existing) -> gsr_sparse_return (peer stores) -- barrier --
+ *             gsr_sparse_backward_preprocess       gather of the returned rows + fused preprocess backward
+ * peer_cand[r] is rank r's candidate workspace (gsr_sparse_candidate_bytes, from gsr_peer_alloc / gsr_peer_open) as
+ * mapped in this process; with virtual ranks on one device they are simply different buffers. */
+typedef struct gsr_sparse_plan {
+  int32_t world, rank;
+  int32_t slice_len; /* ceil(P_total / world): Gaussians per rank (the last rank may hold fewer) */
+  int32_t seg_cap;   /* capacity of one (source -> destination) segment; the same on every rank */
+} gsr_sparse_plan;
+typedef struct gsr_sparse_view_t {
+  void* records;         /* [world*seg_cap] 48-byte candidate records */
+  float* ret;            /* [world*seg_cap, 12] accumulator rows returned by the tile owners */
+  size_t geometry_bytes; /* size of the leading part that is laid out like gsr_geometry_bytes(world*seg_cap) */
+} gsr_sparse_view_t;
+GSR_API size_t gsr_sparse_local_bytes(int32_t slice_len);
+GSR_API size_t gsr_sparse_candidate_bytes(int32_t world, int32_t seg_cap);
+GSR_API int gsr_sparse_view(void* cand_ws, int32_t world, int32_t seg_cap, gsr_sparse_view_t* out);
+GSR_API int gsr_sparse_preprocess(const gsr_settings* s, const gsr_cloud* shard, const gsr_sparse_plan* plan, void* local_ws,
+                          size_t local_bytes, int32_t* radii_local /* [shard.P] */, void* const* peer_cand /* [world] host */,
+                          size_t cand_bytes, int32_t* counts_row /* [GSR_MAX_PEERS] device */, void* stream);
+GSR_API int gsr_sparse_order(const gsr_settings* s, const gsr_sparse_plan* plan, void* cand_ws, size_t cand_bytes,
+                     const int32_t* counts_matrix /* [world, GSR_MAX_PEERS] device, row = source */,
+                     int32_t* radii_cand /* [world*seg_cap] */, int32_t* host_out /* [2] pinned host */, void* stream);
+GSR_API int gsr_sparse_return(const gsr_sparse_plan* plan, const void* acc_cand /* [world*seg_cap, 12] */,
+                      const int32_t* counts_matrix, void* const* peer_cand, void* stream);
+GSR_API int gsr_sparse_backward_preprocess(const gsr_settings* s, const gsr_cloud* shard, const gsr_sparse_plan* plan,
+                                   const void* local_ws, size_t local_bytes, const int32_t* radii_local,
+                                   const void* cand_ws, size_t cand_bytes, void* acc_slice /* [shard.P,12] scratch */,
+                                   size_t acc_bytes, const gsr_grads* grads, void* stream);
+/* Copies the tile rows this rank owns of its [4,H,W] frame (colour + depth) into the frames of all other ranks
+ * (128-bit peer stores): with one writer per pixel this replaces the all-reduce of the frames. A cross-rank barrier
+ * must follow before the frames are read. */
+GSR_API int gsr_frame_broadcast(const gsr_tile_owner* owner, int32_t image_width, int32_t image_height, const float* frame,
+                        void* const* peer_frames /* [world] host */, void* stream);
+
 /* ---- tuning / instrumentation ---------------------------------------------------------------------------
  * gsr_set_option("render_variant", v) etc.; unknown names return GSR_ERR_INVALID.
  * gsr_launch_count(): number of this library's kernel launches (CUB's included) since process start. */

@@ -368,6 +368,29 @@ def test_speculative_second_half_equals_exact_path():
         RZ.SPECULATIVE = True
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_binning_variants_match_reference_lists(variant):
+    """Both binning implementations -- 0: emit kernel + CUB radix sort + tile_ranges (binning.cu), 1: difference-array
+    ranges + two own radix passes with the emission fused in (tile_binning.cu, default) -- must give the reference's
+    point_list / ranges / R bit for bit, incl. a partial last tile row/column and a frame with > 256 tile columns."""
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref not built")
+    _lib.set_option("binning_variant", variant)
+    try:
+        cloud, _ = synth.make_config("c3", P=80_000)
+        for (W, H, k) in [(333, 201, 5), (4160, 48, 1), (1600, 1200, 2)]:
+            cam = synth.ring_cameras(8, 4.5, 15.0, W, H, 61.0)[k]
+            ours = run_ours(cloud, cam, (0.1, 0.2, 0.3))
+            ref = _ref_run(cloud, cam, (0.1, 0.2, 0.3))
+            v, s = ours["views"], ref["state"]
+            assert ours["R"] == ref["R"], (W, H)
+            assert torch.equal(v["ranges"], s["ranges"]), (W, H)
+            assert torch.equal(v["point_list"], s["point_list"]), (W, H)
+            assert torch.equal(ours["color"], ref["color"]), (W, H)
+    finally:
+        _lib.set_option("binning_variant", 1)
+
+
 def test_edit_loop_harness_runs_and_densifies():
     """Config-5 loop shape (2 forwards + 1 backward per step, densification changing P) on a small cloud."""
     from gaussianeditor_b200 import edit_loop

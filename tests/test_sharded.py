@@ -165,13 +165,90 @@ def test_virtual_ranks_tile_the_single_gpu_result(world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("p2p", [False, True])
-def test_two_process_nccl_matches_single_gpu(p2p):
+@pytest.mark.parametrize("world,cap_mode", [(2, "full"), (3, "tight"), (8, "tight"), (8, "overflow")])
+def test_sparse_exchange_virtual_ranks_match_single_gpu(world, cap_mode):
+    """Sparse exchange (csrc/sparse_exchange.cu) with `world` virtual ranks on one GPU: records only travel to the ranks
+    whose tile rows they touch, yet frames, depth, radii and the instance total must equal the single-GPU result bit for
+    bit and the gathered gradients must match to summation order. `tight` uses the smallest legal segment capacity
+    (exactly the largest segment), `overflow` starts too small and must be detected through the count matrix."""
+    from gaussianeditor_b200 import sparse_sharded as SS
+    from util import cloud_tensors, settings_from, rel_l2
+    dev = torch.device("cuda")
+    case = _case()
+    cloud, cam, bg, dL, ref = case["cloud"], case["cam"], case["bg"], case["dL"], case["ref"]
+    H, W = cam.image_height, cam.image_width
+    rs = settings_from(cam, bg, cloud.sh_degree, dev)
+    full = cloud_tensors(cloud, dev)
+    P = cloud.means3D.shape[0]
+    empty = torch.empty(0, device=dev)
+    plans = [S.ShardPlan(P, world, r) for r in range(world)]
+    ranks = [SS.SparseRank(p, dev, W, H) for p in plans]
+    SS.link_virtual(ranks)
+
+    def forward(cap):
+        steps = []
+        for rk in ranks:
+            sl = lambda t: S.shard_slice(t, rk.plan)
+            steps.append(SS.sparse_preprocess(rk, rs, sl(full["means3D"]), sl(full["shs"]), empty, sl(full["opacities"]),
+                                              sl(full["scales"]), sl(full["rotations"]), empty, cap))
+        matrix = torch.stack([rk.matrix for rk in ranks]).sum(0)            # the all-reduce
+        for rk in ranks:
+            rk.matrix.copy_(matrix)
+        out = [SS.sparse_order(st) for st in steps]
+        return steps, matrix, out
+
+    cap0 = ranks[0].cap_alloc
+    steps, matrix, out = forward(cap0)
+    maxc = out[0][1]
+    assert all(o[1] == maxc for o in out) and maxc == int(matrix.max()) and 0 < maxc <= cap0
+    # the sparse exchange really is sparse: far fewer candidates than world * P
+    assert int(matrix.sum()) < 0.75 * world * P
+    if cap_mode == "tight":
+        steps, matrix, out = forward(maxc)
+    elif cap_mode == "overflow":
+        steps, matrix, out = forward(max(1, maxc // 2))
+        assert all(o[1] == maxc and o[1] > st.cap for o, st in zip(out, steps))      # detected on every rank alike
+        steps, matrix, out = forward(SS.next_capacity(maxc, cap0))
+    assert sum(o[0] for o in out) == ref["R"]
+    for rk in ranks:
+        assert torch.equal(rk.radii_local[:rk.plan.count], ref["radii"][rk.plan.base:rk.plan.base + rk.plan.count])
+    # render the owned rows into the local frames, then broadcast them into everybody's frame
+    for rk in ranks:
+        rk.frame.fill_(float("nan"))
+    for st in steps:
+        SS.sparse_render(st, st.rk.frame[:3], st.rk.frame[3:])
+    for rk in ranks:
+        SS.frame_broadcast(rk)
+    torch.cuda.synchronize()
+    for rk in ranks:
+        assert torch.equal(rk.frame[:3], ref["color"]) and torch.equal(rk.frame[3:], ref["depth"]), rk.plan.rank
+    gdL = torch.from_numpy(dL).to(dev)
+    accs = [SS.sparse_backward_render(st, gdL) for st in steps]
+    for st, acc in zip(steps, accs):
+        SS.sparse_return(st, acc)
+    names = ["dmean3D", "dmean2D", "dsh", None, "dopacity", "dscale", "drot", None]
+    for st in steps:
+        p = st.rk.plan
+        grads = SS.sparse_backward_preprocess(st)
+        for name, g in zip(names, grads):
+            if name is None:
+                continue
+            want = ref["grads"][name][p.base:p.base + p.count]
+            assert g.shape == want.shape
+            assert rel_l2(g.cpu().numpy(), want.cpu().numpy()) <= 2e-5, (name, p.rank)
+        vis = ref["radii"][p.base:p.base + p.count] > 0
+        assert float(grads[0][~vis].abs().sum()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["dense-nccl", "dense-p2p", "sparse"])
+def test_two_process_nccl_matches_single_gpu(variant):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    extra = {"dense-nccl": [], "dense-p2p": ["--p2p"], "sparse": ["--mode", "sparse"]}[variant]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, "tools", "sharded_check.py"), "--config", "c3",
-           "--P", "30001"] + (["--p2p"] if p2p else [])
+           "--P", "30001"] + extra
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "SHARDED_CHECK_OK" in r.stdout

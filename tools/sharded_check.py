@@ -25,7 +25,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="c3")
     ap.add_argument("--P", type=int, default=None)
-    ap.add_argument("--p2p", action="store_true", help="fused preprocess + all-gather over peer memory")
+    ap.add_argument("--p2p", action="store_true", help="dense mode: fused preprocess + all-gather over peer memory")
+    ap.add_argument("--mode", default="dense", choices=["dense", "sparse"])
     a = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dev = torch.device("cuda", local)
@@ -44,7 +45,7 @@ def main():
                                                 shs=full["shs"], scales=full["scales"], rotations=full["rotations"])
     (color * dL).sum().backward()
 
-    rast = S.ShardedGaussianRasterizer(rs, P, p2p=a.p2p)
+    rast = S.ShardedGaussianRasterizer(rs, P, p2p=(True if a.mode == 'sparse' else a.p2p), mode=a.mode)
     plan = rast.plan
     loc = {k: S.shard_slice(v.detach(), plan).clone().requires_grad_(True) for k, v in full.items()}
     lm2 = torch.zeros_like(loc["means3D"], requires_grad=True)
@@ -72,7 +73,7 @@ def main():
                                           scales=full["scales"].detach(), rotations=full["rotations"].detach())
     two_ok = torch.equal(c1, color) and torch.equal(c2, ref_c2)
     del c1, c2
-    if a.p2p:  # second round through the recycled peer workspace
+    if a.p2p or a.mode == 'sparse':  # second round through the recycled peer workspace
         for v in list(loc.values()) + [lm2]:
             v.grad = None
         del scolor, sradii, sdepth
@@ -89,11 +90,18 @@ def main():
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"world={world} p2p={a.p2p} P={P} R_rank0={S._ShardedRasterize.last_R} worst_grad_rel_l2={worst:.2e}")
+        extra = ""
+        if a.mode == "sparse":
+            from gaussianeditor_b200 import sparse_sharded as SS
+            extra = f" sparse={SS._SparseShardedRasterize.last} redo={rast.sparse_pool.redo}"
+        else:
+            extra = f" R_rank0={S._ShardedRasterize.last_R}"
+        print(f"world={world} mode={a.mode} p2p={a.p2p} P={P}{extra} worst_grad_rel_l2={worst:.2e}")
         print("SHARDED_CHECK_OK" if int(flag) == 1 else "SHARDED_CHECK_FAILED")
-    if rast.pool is not None:
-        del scolor, sradii, sdepth
-        rast.pool.close()
+    del scolor, sradii, sdepth
+    import gc
+    gc.collect()
+    rast.close()
     dist.destroy_process_group()
     sys.exit(0 if int(flag) == 1 else 1)
 
