@@ -408,6 +408,24 @@ def sharded_config4(dist, dev, rank, world, steps, warmup, points=None):
     reps = sorted(timed(sharded_step, steps) for _ in range(3))
     ms_sharded = reps[1]
     frames = [sharded_step(i, keep=True) for i in range(len(rs))]
+    # per-phase device time (CUDA events between the phases of the autograd path; separate pass, max over ranks)
+    phases = None
+    if rast.mode == "sparse":
+        from gaussianeditor_b200 import sparse_sharded as SS
+        acc = {}
+        nph = 8
+        for i in range(nph):
+            SS.TRACE = []
+            sharded_step(i)
+            torch.cuda.synchronize()
+            tr = SS.TRACE
+            for (n0, e0), (n1, e1) in zip(tr[:-1], tr[1:]):
+                acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / nph
+        SS.TRACE = None
+        names = list(acc.keys())
+        t = torch.tensor([acc[n] for n in names], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases = {n: round(float(v), 4) for n, v in zip(names, t.tolist())}
     out = None
     # plain single-GPU rasterizer on the full cloud, rank 0 only (the others wait at the barrier below)
     if rank == 0:
@@ -441,6 +459,8 @@ def sharded_config4(dist, dev, rank, world, steps, warmup, points=None):
                "plain_1gpu_mpix_s": W * H / (ms_plain * 1e-3) / 1e6, "vs_1gpu_plain": ms_plain / ms_sharded,
                "image_equals_1gpu": bool(same), "frames_compared": len(rs), "grad_rel_l2_vs_1gpu_max": gerr,
                "scaling": "strong"}
+        if phases:
+            out["phase_ms_max_over_ranks"] = phases
         if rast.mode == "sparse":
             from gaussianeditor_b200 import sparse_sharded as SS
             last = SS._SparseShardedRasterize.last
@@ -468,6 +488,7 @@ def main():
     ap.add_argument("--config", default="c3")
     ap.add_argument("--points", type=int, default=None, help="override the Gaussian count (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], help="library tuning option k=v (A/B measurements only)")
     ap.add_argument("--no-sharded", action="store_true", help="skip the config-4 Gaussian-sharded leg at --gpus N > 1")
     ap.add_argument("--sharded-points", type=int, default=None, help="override config 4's Gaussian count (debug only)")
     args = ap.parse_args()
@@ -520,6 +541,9 @@ def main():
     wl = Workload(name, dev, P=args.points)
     runner = OursRunner(wl) if args.impl == "ours" else ReferenceCudaRunner(wl)
     from gaussianeditor_b200 import _lib
+    for kv in args.option:
+        k, v = kv.split("=")
+        _lib.set_option(k, int(v))
     npix = wl.W * wl.H
 
     def barrier():

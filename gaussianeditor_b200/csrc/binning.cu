@@ -54,15 +54,6 @@ __device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx
   rmax.y = (unsigned)min(gy, max((int)0, (int)((py + radius + TILE - 1) / TILE)));
 }
 
-// the four corners of a tile rectangle in the (gy+1) x (gx+1) difference array (tile_binning.cu: tile_prefix_kernel)
-__device__ __forceinline__ void add_tile_rect(int32_t* diff, int gx, uint2 rmin, uint2 rmax) {
-  const int stride = gx + 1;
-  atomicAdd(diff + rmin.y * stride + rmin.x, 1);
-  atomicAdd(diff + rmin.y * stride + rmax.x, -1);
-  atomicAdd(diff + rmax.y * stride + rmin.x, -1);
-  atomicAdd(diff + rmax.y * stride + rmax.x, 1);
-}
-
 // Rows of the rectangle [rmin.y, rmax.y) this rank owns (ty % stride == phase): first owned row and their number.
 __device__ __forceinline__ void owned_rows(uint32_t ymin, uint32_t ymax, int stride, int phase, uint32_t& y0, uint32_t& ny) {
   if (stride == 1) { y0 = ymin; ny = ymax - ymin; return; }
@@ -81,7 +72,7 @@ __device__ __forceinline__ void owned_rows(uint32_t ymin, uint32_t ymax, int str
 __global__ void retouch_kernel(int P, const SplatRecord* __restrict__ records, int gx, int gy, int stride, int phase,
                                int32_t* __restrict__ radii, uint32_t* __restrict__ tiles_touched,
                                uint32_t* __restrict__ ident, uint32_t* __restrict__ depth_keys,
-                               int32_t* __restrict__ tile_diff) {
+                               int32_t* __restrict__ tile_diff, int diff_copies) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t n = 0;
   if (idx < P) {
@@ -97,7 +88,8 @@ __global__ void retouch_kernel(int P, const SplatRecord* __restrict__ records, i
       n = ny * (rmax.x - rmin.x);
       if (n != 0) {
         key = __float_as_uint(__ldg(r + 1).z);
-        if (tile_diff) add_tile_rect(tile_diff, gx, rmin, rmax);  // full rectangle: tile_prefix_kernel keeps the owned rows
+        // full rectangle: tile_prefix_kernel keeps the owned rows
+        if (tile_diff) add_tile_rect(tile_diff, gx, gy, diff_copies, (uint32_t)idx, rmin.x, rmin.y, rmax.x, rmax.y);
       }
     }
     radii[idx] = radius;
@@ -429,7 +421,7 @@ int launch_retouch(const gsr_settings& s, int P, const GeometryWS& g, int32_t* r
     if (rc) return rc;
   }
   retouch_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, g.records, gx, gy, own.stride, own.phase, radii, g.tiles_touched,
-                                                  g.ident, g.depth_keys, v2 ? g.tile_diff : nullptr);
+                                                  g.ident, g.depth_keys, v2 ? g.tile_diff : nullptr, tile_diff_copies(gx, gy));
   g_launches++;
   return check_launch("retouch", s.debug != 0, st);
 }

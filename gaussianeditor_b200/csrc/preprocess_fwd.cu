@@ -61,6 +61,7 @@ struct PreArgs {
   // its tile rectangle to a 2-D difference array (its 2-D prefix sum is the per-tile instance count -> tile ranges and
   // the radix histograms, its weighted sum is R). Null in the sharded paths (the tile owner does it).
   int32_t* tile_diff;
+  int diff_copies;
   int vec_ok;  // means3D and scales are 16-byte aligned: full blocks use 128-bit cooperative loads
 };
 
@@ -150,6 +151,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
       }
     }
   }
+  // this thread's own rotation / opacity are requested before the barrier too, so that all of the kernel's first-touch
+  // loads are in flight together (one exposed memory latency instead of one per dependent stage)
+  float4 q_pref = make_float4(0.f, 0.f, 0.f, 0.f);
+  float op_pref = 0.f;
+  if (live) {
+    if (a.rotations != nullptr) q_pref = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+    op_pref = a.opacities[idx];
+  }
   if (!(BULK_SH || RAW)) __syncthreads();  // the other variants synchronise right below (mbarrier init)
 
   if (BULK_SH || RAW) {
@@ -186,6 +195,33 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     }
   }
 
+  // ---- projection (forward.cu:196-200) ----
+  float2 p_proj = make_float2(0.f, 0.f);
+  if (vis) {
+    const float* pm = a.proj;
+    float4 p_hom;
+    p_hom.x = __fadd_rn(__fmaf_rn(pm[8], p_orig.z, __fmaf_rn(pm[0], p_orig.x, __fmul_rn(pm[4], p_orig.y))), pm[12]);
+    p_hom.y = __fadd_rn(__fmaf_rn(pm[9], p_orig.z, __fmaf_rn(pm[1], p_orig.x, __fmul_rn(pm[5], p_orig.y))), pm[13]);
+    p_hom.w = __fadd_rn(__fmaf_rn(pm[11], p_orig.z, __fmaf_rn(pm[3], p_orig.x, __fmul_rn(pm[7], p_orig.y))), pm[15]);
+    float p_w = __frcp_rn(__fadd_rn(p_hom.w, 0.0000001f));
+    p_proj = make_float2(__fmul_rn(p_hom.x, p_w), __fmul_rn(p_hom.y, p_w));
+  }
+  // The SH row is fetched by the TMA unit NOW, while the thread does the covariance math -- but only for Gaussians
+  // whose centre projects onto the screen or its near surroundings (|ndc| <= 1.15): the ~20 % that pass the z test
+  // far off-screen would be fetched for nothing (they almost never produce a tile). A Gaussian outside that band that
+  // does reach the screen (a huge splat) reads its row with plain loads below: same values, same arithmetic.
+  const bool likely = vis && fabsf(p_proj.x) <= 1.15f && fabsf(p_proj.y) <= 1.15f;
+  if (BULK_SH) {
+    // everybody arrives exactly once on the CTA barrier
+    const uint32_t nbytes = (uint32_t)(((a.D + 1) * (a.D + 1) * 12 + 15) & ~15);
+    if (likely && want_sh) {
+      mbar_arrive_expect_tx(&bar, nbytes);
+      bulk_g2s(&sh_rows[threadIdx.x * SH_ROW_WORDS], a.shs + (size_t)idx * a.M * 3, nbytes, &bar);
+    } else {
+      mbar_arrive(&bar);
+    }
+  }
+
   int my_radius_i = 0;
   uint32_t tiles = 0;
   uint32_t depth_key = 0xFFFFFFFFu;
@@ -194,14 +230,6 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
   bool emit = false;
 
   if (vis) {
-    // ---- projection (forward.cu:196-200) ----
-    const float* pm = a.proj;
-    float4 p_hom;
-    p_hom.x = __fadd_rn(__fmaf_rn(pm[8], p_orig.z, __fmaf_rn(pm[0], p_orig.x, __fmul_rn(pm[4], p_orig.y))), pm[12]);
-    p_hom.y = __fadd_rn(__fmaf_rn(pm[9], p_orig.z, __fmaf_rn(pm[1], p_orig.x, __fmul_rn(pm[5], p_orig.y))), pm[13]);
-    p_hom.w = __fadd_rn(__fmaf_rn(pm[11], p_orig.z, __fmaf_rn(pm[3], p_orig.x, __fmul_rn(pm[7], p_orig.y))), pm[15]);
-    float p_w = __frcp_rn(__fadd_rn(p_hom.w, 0.0000001f));
-    float2 p_proj = make_float2(__fmul_rn(p_hom.x, p_w), __fmul_rn(p_hom.y, p_w));
 
     // ---- 3-D covariance (forward.cu:118-152); the quaternion is used as given ----
     // From here to the conic every operation is pinned with _rn intrinsics to the exact sequence nvcc emits for
@@ -215,7 +243,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
       for (int k = 0; k < 6; k++) cov3D[k] = a.cov3D_precomp[(size_t)idx * 6 + k];
     } else {
       float3 scale = make_float3(s_scale[3 * threadIdx.x], s_scale[3 * threadIdx.x + 1], s_scale[3 * threadIdx.x + 2]);
-      float4 q = __ldg(reinterpret_cast<const float4*>(a.rotations) + idx);
+      float4 q = q_pref;
       if (RAW) {
         scale = make_float3(expf(scale.x), expf(scale.y), expf(scale.z));
         const float n = fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);  // F.normalize eps
@@ -312,21 +340,8 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
         my_radius_i = max_radius;
         depth_key = __float_as_uint(p_view.z);
         rec.q0 = make_float4(point_image.x, point_image.y, conic.x, conic.y);
-        rec.q1 = make_float4(conic.z, RAW ? sigmoid_act(a.opacities[idx]) : a.opacities[idx], p_view.z, 0.f);
+        rec.q1 = make_float4(conic.z, RAW ? sigmoid_act(op_pref) : op_pref, p_view.z, 0.f);
       }
-    }
-  }
-
-  if (BULK_SH) {
-    // One TMA row fetch per Gaussian that will emit a record (in front of the near plane AND a non-empty tile
-    // rectangle: the ~20 % that pass the z test but miss the screen never touch their SH bytes); everybody arrives
-    // exactly once on the CTA barrier. The latency of the fetch is covered by the other resident CTAs (8 per SM).
-    const uint32_t nbytes = (uint32_t)(((a.D + 1) * (a.D + 1) * 12 + 15) & ~15);
-    if (emit && want_sh) {
-      mbar_arrive_expect_tx(&bar, nbytes);
-      bulk_g2s(&sh_rows[threadIdx.x * SH_ROW_WORDS], a.shs + (size_t)idx * a.M * 3, nbytes, &bar);
-    } else {
-      mbar_arrive(&bar);
     }
   }
 
@@ -348,7 +363,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
       float w[16];
       sh_weights(a.D, dir.x, dir.y, dir.z, w);
       float res[3];
-      if (BULK_SH) {
+      if (BULK_SH && likely) {
         const float* row = &sh_rows[threadIdx.x * SH_ROW_WORDS];
         // pull the row into registers with 128-bit shared loads (row stride 208 B: conflict-free)
         float v[48];
@@ -410,13 +425,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_fwd_kernel(const PreAr
     }
   }
   if (a.tile_diff != nullptr) {
-    if (emit) {
-      const int stride = a.gx + 1;
-      atomicAdd(a.tile_diff + rect_min.y * stride + rect_min.x, 1);
-      atomicAdd(a.tile_diff + rect_min.y * stride + rect_max.x, -1);
-      atomicAdd(a.tile_diff + rect_max.y * stride + rect_min.x, -1);
-      atomicAdd(a.tile_diff + rect_max.y * stride + rect_max.x, 1);
-    }
+    if (emit) add_tile_rect(a.tile_diff, a.gx, a.gy, a.diff_copies, (uint32_t)idx, rect_min.x, rect_min.y, rect_max.x, rect_max.y);
   }
   if (live) {
     a.radii[idx] = my_radius_i;
@@ -458,6 +467,7 @@ int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const Geome
   a.depth_keys = g.depth_keys; a.ident = g.ident; a.radii = radii;
   a.vec_ok = ((reinterpret_cast<uintptr_t>(c.means3D) | reinterpret_cast<uintptr_t>(c.scales)) & 15) == 0;
   a.tile_diff = count_tiles ? g.tile_diff : nullptr;
+  a.diff_copies = tile_diff_copies(a.gx, a.gy);
   const int grid = (c.P + PRE_THREADS - 1) / PRE_THREADS;
   // TMA row fetch needs 16-byte aligned rows: M*12 % 16 == 0 and an aligned base pointer.
   const bool bulk = g_opt.preprocess_variant >= 1 && c.colors_precomp == nullptr && c.shs != nullptr &&

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(SP_THREADS) sparse_push_kernel(const PushArgs 
 __global__ void retouch_sparse_kernel(int world, int cap, int me, const int32_t* __restrict__ counts_matrix,
                                       const SplatRecord* __restrict__ records, int gx, int gy, int32_t* __restrict__ radii,
                                       uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ ident,
-                                      uint32_t* __restrict__ depth_keys, int32_t* __restrict__ tile_diff) {
+                                      uint32_t* __restrict__ depth_keys, int32_t* __restrict__ tile_diff, int diff_copies) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = c < world * cap;
   const int s = live ? c / cap : 0, j = c - s * cap;
@@ -268,13 +268,8 @@ __global__ void retouch_sparse_kernel(int world, int cap, int me, const int32_t*
       n = ny * (xmax - xmin);
       if (n != 0) {
         key = __float_as_uint(__ldg(r + 1).z);
-        if (tile_diff) {  // full rectangle; tile_prefix_kernel keeps the owned rows
-          const int stride = gx + 1;
-          atomicAdd(tile_diff + ymin * stride + xmin, 1);
-          atomicAdd(tile_diff + ymin * stride + xmax, -1);
-          atomicAdd(tile_diff + ymax * stride + xmin, -1);
-          atomicAdd(tile_diff + ymax * stride + xmax, 1);
-        }
+        // full rectangle; tile_prefix_kernel keeps the owned rows
+        if (tile_diff) add_tile_rect(tile_diff, gx, gy, diff_copies, (uint32_t)c, xmin, ymin, xmax, ymax);
       }
     }
   }
@@ -450,7 +445,7 @@ int gsr_sparse_order(const gsr_settings* s, const gsr_sparse_plan* plan, void* c
   if (v2 && (rc = clear_tile_counts(sc.g, gx, gy, st))) return rc;
   retouch_sparse_kernel<<<(M + 255) / 256, 256, 0, st>>>(plan->world, plan->seg_cap, plan->rank, counts_matrix, sc.g.records,
                                                          gx, gy, radii_cand, sc.g.tiles_touched, sc.g.ident, sc.g.depth_keys,
-                                                         v2 ? sc.g.tile_diff : nullptr);
+                                                         v2 ? sc.g.tile_diff : nullptr, tile_diff_copies(gx, gy));
   if (v2) {
     TileOwner own; own.stride = plan->world; own.phase = plan->rank;
     if ((rc = launch_tile_count(sc.g, gx, gy, own, st))) return rc;

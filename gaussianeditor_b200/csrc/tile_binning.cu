@@ -76,18 +76,25 @@ __device__ __forceinline__ int owned_rows_from(int y, int gy, int stride, int ph
   return first < gy ? (gy - first + stride - 1) / stride : 0;
 }
 
-// R without any prefix sum: an entry (x, y) of the difference array is seen by every tile (tx >= x, ty >= y), so
-//   R = sum diff[y][x] * (gx - x) * #owned rows >= y.
-__global__ void __launch_bounds__(PREFIX_THREADS)
-tile_count_kernel(int gx, int gy, int own_stride, int own_phase, const int32_t* __restrict__ diff, uint32_t* __restrict__ R_dev) {
-  __shared__ long long s_part[PREFIX_THREADS / 32];
-  const int stride = gx + 1, n = stride * (gy + 1);
+// One thread per entry of the difference array: adds up the replicas (-> `sum`, what tile_prefix_kernel reads) and
+// accumulates R without any prefix sum: an entry (x, y) is seen by every tile (tx >= x, ty >= y), so
+//   R = sum_entries diff[y][x] * (gx - x) * #owned rows >= y.
+// Every Gaussian's four corners cancel to its own instance count, so each block's partial sum is non-negative.
+constexpr int COUNT_THREADS = 256;
+__global__ void __launch_bounds__(COUNT_THREADS)
+tile_count_kernel(int gx, int gy, int own_stride, int own_phase, const int32_t* __restrict__ diff, int copies,
+                  int32_t* __restrict__ sum, uint32_t* __restrict__ R_dev) {
+  __shared__ long long s_part[COUNT_THREADS / 32];
+  const int stride = gx + 1, nent = stride * (gy + 1);
+  const int i = blockIdx.x * COUNT_THREADS + threadIdx.x;
   long long acc = 0;
-  for (int i = threadIdx.x; i < n; i += PREFIX_THREADS) {
-    const int v = diff[i];
+  if (i < nent) {
+    int v = 0;
+    for (int c = 0; c < copies; c++) v += diff[(size_t)c * nent + i];  // independent coalesced loads
+    sum[i] = v;
     if (v != 0) {
       const int y = i / stride, x = i - y * stride;
-      acc += (long long)v * (long long)(gx - x) * (long long)owned_rows_from(y, gy, own_stride, own_phase);
+      acc = (long long)v * (long long)(gx - x) * (long long)owned_rows_from(y, gy, own_stride, own_phase);
     }
   }
 #pragma unroll
@@ -95,10 +102,11 @@ tile_count_kernel(int gx, int gy, int own_stride, int own_phase, const int32_t* 
   if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x < 32) {
-    long long v = s_part[threadIdx.x];
+    long long v = threadIdx.x < COUNT_THREADS / 32 ? s_part[threadIdx.x] : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) R_dev[0] = (uint32_t)v;
+    // signed partial sums of different blocks add up to R >= 0 (two's complement wrap-around is harmless)
+    if (threadIdx.x == 0 && v != 0) atomicAdd(R_dev, (uint32_t)v);
   }
 }
 
@@ -114,12 +122,18 @@ tile_prefix_kernel(int gx, int gy, int own_stride, int own_phase, const int32_t*
   const int stride = gx + 1;
   int32_t* cnt = stride * (gy + 1) <= SMEM_CNT ? s_cnt : cnt_global;
   for (int i = tid; i < 2 * NB; i += PREFIX_THREADS) (&s_h[0][0])[i] = 0;
-  // prefix along x: one warp per row, 32 entries per step (coalesced) with a shuffle scan and a running carry
+  // prefix along x: one warp per row, 32 entries per step with a shuffle scan and a running carry. With the array in
+  // shared memory the difference array is first copied in with independent coalesced loads (one exposed latency).
+  const int nent = stride * (gy + 1);
+  // the summed difference array (tile_count_kernel) -> shared memory, or -> the global scratch for very large grids
+  for (int i = tid; i < nent; i += PREFIX_THREADS) cnt[i] = diff[i];
+  __syncthreads();
+  const int32_t* src = cnt;
   for (int r = warp; r <= gy; r += PREFIX_THREADS / 32) {
     int carry = 0;
     for (int x0 = 0; x0 <= gx; x0 += 32) {
       const int x = x0 + lane;
-      int v = x <= gx ? diff[r * stride + x] : 0;
+      int v = x <= gx ? src[r * stride + x] : 0;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const int u = __shfl_up_sync(0xffffffffu, v, o);
@@ -176,14 +190,27 @@ tile_prefix_kernel(int gx, int gy, int own_stride, int own_phase, const int32_t*
   // speculative launch whose capacity guess was too small: the sort passes skip their work and the host redoes the
   // second half; empty ranges keep the (discarded) render of this launch away from the unsorted list
   const bool overflow = R_dev != nullptr && __ldcg(R_dev) > cap;
+  // ranges + histogram of the HIGH digit: a thread's consecutive tiles share it except at a boundary -> one shared
+  // atomic per run instead of one per tile (7500 atomics into 64 bins serialised this kernel)
+  uint32_t hi_bin = 0xFFFFFFFFu, hi_sum = 0;
   for (int t = t0; t < t1; t++) {
     const uint32_t c = overflow ? 0u : count_of(t);
     ranges[t] = c ? make_uint2(run, run + c) : make_uint2(0u, 0u);
-    if (c) {
-      atomicAdd(&s_h[0][t & mask1], c);
-      atomicAdd(&s_h[1][(uint32_t)t >> bits1], c);
+    const uint32_t b = (uint32_t)t >> bits1;
+    if (b != hi_bin) {
+      if (hi_sum) atomicAdd(&s_h[1][hi_bin], hi_sum);
+      hi_bin = b; hi_sum = 0;
     }
+    hi_sum += c;
     run += c;
+  }
+  if (hi_sum) atomicAdd(&s_h[1][hi_bin], hi_sum);
+  // histogram of the LOW digit: thread `tid` adds up the tiles t = tid, tid + 1024, ... -- they all have the low digit
+  // tid & mask1 (1024 is a multiple of 2^bits1) -> one shared atomic per thread
+  if (!overflow) {
+    uint32_t lo_sum = 0;
+    for (int t = tid; t < ntile; t += PREFIX_THREADS) lo_sum += count_of(t);
+    if (lo_sum) atomicAdd(&s_h[0][tid & mask1], lo_sum);
   }
   __syncthreads();
   if (warp < 2) {  // exclusive scan of one 256-bin histogram per warp (8 bins per lane)
@@ -271,29 +298,70 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
       }
       const int r_lo = lo;
       uint32_t* soff = s_vals + warp * (32 * SORT_ITEMS);
+      uint16_t* skey = s_keys + warp * (32 * SORT_ITEMS);
 #pragma unroll
       for (int i = 0; i < SORT_ITEMS; i++) soff[i * 32 + lane] = __ldg(a.offsets + min(r_lo + i * 32 + lane, a.P - 1));
       __syncwarp();
+      // BLOCKED generation: lane l walks the 16 consecutive slots s_begin + 16 l ... -- one binary search for its first
+      // slot, then tile ids by incrementing (column, row) inside the Gaussian's rectangle; a new Gaussian is fetched
+      // only when the walk crosses the end of the current one (every visible rank owns >= 1 slot: one step).
+      const uint32_t first = s_begin + (uint32_t)(SORT_ITEMS * lane);
+      const uint32_t sc = min(first, R - 1);
+      int j = 0;  // smallest j with soff[j] > sc
 #pragma unroll
-      for (int i = 0; i < SORT_ITEMS; i++) {
-        const uint32_t s = min(s_begin + 32u * i + lane, R - 1);
-        int j = 0;  // smallest j with soff[j] > s
-#pragma unroll
-        for (int step = 256; step > 0; step >>= 1)
-          if (soff[j + step - 1] <= s) j += step;
-        const uint32_t end = soff[j];
-        const uint32_t idx = __ldg(a.order + min(r_lo + j, a.P - 1));
-        const uint32_t start = end - __ldg(a.tiles_touched + idx);
+      for (int step = 256; step > 0; step >>= 1)
+        if (soff[j + step - 1] <= sc) j += step;
+      uint32_t idx, end, w, xmin, ybase, rx, ry;
+      auto fetch = [&](int jj) {
+        end = soff[jj];
+        idx = __ldg(a.order + min(r_lo + jj, a.P - 1));
         const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.records + idx));
         uint2 rmin, rmax;
         tile_rect(q0.x, q0.y, __ldg(a.radii + idx), a.gx, a.gy, rmin, rmax);
-        const uint32_t w = max(rmax.x - rmin.x, 1u);
-        const uint32_t k = s - start;
-        const uint32_t ry = k / w, rx = k - ry * w;
+        w = max(rmax.x - rmin.x, 1u);
+        xmin = rmin.x;
         uint32_t y0, ny;
         owned_rows(rmin.y, rmax.y, a.own_stride, a.own_phase, y0, ny);
-        key[i] = (uint16_t)((y0 + ry * (uint32_t)a.own_stride) * a.gx + (rmin.x + rx));
-        val[i] = idx;
+        ybase = y0;
+      };
+      fetch(j);
+      {
+        const uint32_t k = sc - (end - __ldg(a.tiles_touched + idx));
+        ry = k / w;
+        rx = k - ry * w;
+      }
+      uint16_t bkey[SORT_ITEMS];
+      uint32_t bval[SORT_ITEMS];
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        const uint32_t sl = first + i;
+        if (sl < R && sl >= end) {  // crossed into the next depth rank
+          j++;
+          fetch(j);
+          rx = 0; ry = 0;
+        }
+        bkey[i] = (uint16_t)((ybase + ry * (uint32_t)a.own_stride) * a.gx + (xmin + rx));
+        bval[i] = idx;
+        rx++;
+        if (rx == w) { rx = 0; ry++; }
+      }
+      __syncwarp();  // everybody is done with the staged offsets: their shared memory now carries the transposition
+      // blocked -> warp-striped (the stable ranking below needs item i of lane l to be slot 32 i + l); the XOR swizzle
+      // makes both the writes (stride 16) and the reads (stride 1) bank-conflict free
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        const int pl = SORT_ITEMS * lane + i;
+        const int ph = pl ^ ((pl >> 5) & 15);
+        soff[ph] = bval[i];
+        skey[ph] = bkey[i];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < SORT_ITEMS; i++) {
+        const int pl = 32 * i + lane;
+        const int ph = pl ^ ((pl >> 5) & 15);
+        val[i] = soff[ph];
+        key[i] = skey[ph];
       }
     } else {
 #pragma unroll
@@ -315,7 +383,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
   for (int i = 0; i < SORT_ITEMS; i++) {
     const bool valid = s_begin + 32u * i + lane < R;
     const uint32_t d = valid ? (((uint32_t)key[i] >> a.shift) & dmask) : 0xFFFFFFFFu;
-    const uint32_t peers = __match_any_sync(F, d);
+    // lanes with the same digit: one ballot per digit bit (MATCH.ANY measured ~100 cycles of SM time per warp
+    // instruction here: 16 of them per thread were 40 % of this kernel's stall samples)
+    uint32_t peers = __ballot_sync(F, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      if (b < a.nbits) {  // warp-uniform
+        const uint32_t bal = __ballot_sync(F, (d >> b) & 1u);
+        peers &= ((d >> b) & 1u) ? bal : ~bal;
+      }
+    }
     const uint32_t lt = peers & ((1u << lane) - 1u);
     uint32_t prev = 0;
     if (valid) prev = whist[d];
@@ -376,9 +453,10 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
     } else {
       *st = cta_hist | FLAG_AGG;
       // Windowed look-back: the status words of LB_WINDOW predecessors are fetched with independent loads before any
-      // of them is inspected. In the first wave all CTAs publish their aggregates at the same time and tile k has to
-      // walk back over k of them; one dependent L2 round trip per predecessor made that walk the critical path.
-      constexpr int LB_WINDOW = 8;
+      // of them is inspected. The "inclusive" front can only advance LB_WINDOW tiles per L2 round trip (a tile that
+      // sees nothing but aggregates in its window has to go one window further back), and with ~1600 tiles of a few
+      // microseconds each that chain, not the sorting work, was the critical path (measured: 8 -> 0.34 us per round).
+      constexpr int LB_WINDOW = 32;
       bool done = false;
       for (int p = (int)tile - 1; !done && p >= 0; p -= LB_WINDOW) {
         uint32_t v[LB_WINDOW];
@@ -420,12 +498,14 @@ bool tile_binning_supported(int gx, int gy) {
 
 int clear_tile_counts(const GeometryWS& g, int gx, int gy, cudaStream_t st) {
   // R_dev (16 bytes) sits directly in front of the difference array
-  const size_t bytes = 16 + (size_t)(gx + 1) * (gy + 1) * sizeof(int32_t);
+  const size_t bytes = 16 + (size_t)tile_diff_copies(gx, gy) * (gx + 1) * (gy + 1) * sizeof(int32_t);
   return check_cuda(cudaMemsetAsync(g.R_dev, 0, bytes, st), "tile-count memset");
 }
 
 int launch_tile_count(const GeometryWS& g, int gx, int gy, const TileOwner& own, cudaStream_t st) {
-  tile_count_kernel<<<1, PREFIX_THREADS, 0, st>>>(gx, gy, own.stride, own.phase, g.tile_diff, g.R_dev);
+  const int copies = tile_diff_copies(gx, gy), nent = (gx + 1) * (gy + 1);
+  tile_count_kernel<<<(nent + COUNT_THREADS - 1) / COUNT_THREADS, COUNT_THREADS, 0, st>>>(
+      gx, gy, own.stride, own.phase, g.tile_diff, copies, g.tile_diff + (size_t)copies * nent, g.R_dev);
   g_launches++;
   return check_launch("tile_count", false, st);
 }
@@ -448,7 +528,8 @@ int run_tile_binning(const gsr_settings& s, int P, int R, bool speculative, cons
     StageScope t(ST_RANGES, st);
     cudaError_t e = cudaMemsetAsync(b.sort_state, 0, (1024 + state_words) * sizeof(uint32_t), st);
     if (e != cudaSuccess) return check_cuda(e, "sort-state memset");
-    tile_prefix_kernel<<<1, PREFIX_THREADS, 0, st>>>(gx, gy, own.stride, own.phase, g.tile_diff, cnt, im.ranges, digit_base,
+    const int32_t* diff_sum = g.tile_diff + (size_t)tile_diff_copies(gx, gy) * (gx + 1) * (gy + 1);
+    tile_prefix_kernel<<<1, PREFIX_THREADS, 0, st>>>(gx, gy, own.stride, own.phase, diff_sum, cnt, im.ranges, digit_base,
                                                     bits1, speculative ? g.R_dev : nullptr, (uint32_t)R);
     g_launches++;
     int rc = check_launch("tile_prefix", debug, st);

@@ -126,7 +126,7 @@ def run_edit_loop(rasterizer_cls, steps=200, P=None, device="cuda", densificatio
                 img = GR.render(v, scene, pipe, bg)["render"]
                 targets.append((img + 0.05 * torch.randn(img.shape, generator=g, device=device)).clamp(0, 1))
         render_ms = 0.0
-        counts = []
+        counts, losses, radii_trace = [], [], []
         rng = np.random.default_rng(seed)
         torch.cuda.synchronize()
         t_all0, t_all1 = ev(), ev()
@@ -152,7 +152,9 @@ def run_edit_loop(rasterizer_cls, steps=200, P=None, device="cuda", densificatio
                 scene.max_radii2D[vis] = torch.max(scene.max_radii2D[vis], pkg["radii"][vis].float())
                 scene.add_densification_stats(pkg["viewspace_points"].grad, vis)
             scene.optimizer.step()
+            losses.append(loss.detach())
             if step % densification_interval == 0 and step < steps:
+                radii_trace.append(scene.max_radii2D.clone())   # what the reference's prune test reads (:790-795)
                 scene.densify_and_prune()
             counts.append(scene._xyz.shape[0])
         t_all1.record()
@@ -163,4 +165,6 @@ def run_edit_loop(rasterizer_cls, steps=200, P=None, device="cuda", densificatio
     finally:
         GR.GaussianRasterizer = old
     return dict(steps=steps, total_ms=total_ms, render_ms=render_ms, render_fraction=render_ms / total_ms,
-                ms_per_step=total_ms / steps, P_first=counts[0], P_last=counts[-1], final_loss=float(loss.detach()))
+                ms_per_step=total_ms / steps, P_first=counts[0], P_last=counts[-1], final_loss=float(loss.detach()),
+                counts=counts, losses=torch.stack(losses).cpu().tolist(), max_radii2D=scene.max_radii2D.cpu(),
+                max_radii2D_at_densify=[r.cpu() for r in radii_trace])

@@ -473,11 +473,12 @@ class ShardedGaussianRasterizer(nn.Module):
     ``mode``: ``"sparse"`` (default when peer mappings are available) -- records, the depth sort and the gradient rows
     only involve the ranks whose tile rows a Gaussian touches (sparse_sharded.py); ``"dense"`` -- every rank receives,
     sorts and reduces all P_total records (fused peer-store all-gather with ``p2p=True``, NCCL all-gather otherwise).
-    ``max_in_flight``: forwards whose autograd state may be alive at the same time (GaussianEditor: 2).
+    ``max_in_flight``: forwards whose autograd state may be alive at the same time (GaussianEditor: 2; the peer-mapped
+    workspaces are created collectively up front, one per slot).
     """
 
     def __init__(self, raster_settings: GaussianRasterizationSettings, P_total: int, group=None,
-                 p2p: Optional[bool] = None, mode: Optional[str] = None, max_in_flight: int = 2):
+                 p2p: Optional[bool] = None, mode: Optional[str] = None, max_in_flight: int = 3):
         super().__init__()
         self.raster_settings = raster_settings
         self.exchange = Exchange(group)

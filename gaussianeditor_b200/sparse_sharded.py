@@ -296,15 +296,29 @@ class SparsePool:
         self.all, self.free = [], []
 
 
+TRACE = None   # set to a list to collect (phase name, CUDA event) marks of the autograd path (bench.py, diagnostics)
+
+
+def _mark(name: str):
+    if TRACE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        TRACE.append((name, ev))
+
+
 class _SparseShardedRasterize(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, rs, pool, exchange):
         rk = pool.take()
         device = means3D.device
+        _mark("start")
         while True:
             st = sparse_preprocess(rk, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, pool.cap)
+            _mark("preprocess+push")
             exchange.all_reduce_sum(rk.matrix)             # counts + barrier: every push has landed
+            _mark("count all-reduce")
             R, max_count = sparse_order(st)
+            _mark("order")
             if max_count <= st.cap:
                 break
             pool.redo += 1                                  # same decision on every rank (the matrix is global)
@@ -315,9 +329,11 @@ class _SparseShardedRasterize(torch.autograd.Function):
         # no zero-fill -- and must not get one: a faster peer may already have stored its rows here.
         frame = rk.frame
         sparse_render(st, frame[:3], frame[3:])
+        _mark("bin+blend")
         frame_broadcast(rk)
         exchange.barrier(device)
         out = frame.clone()                                 # the peer-visible frame is overwritten by the next step
+        _mark("frame broadcast+barrier")
         ctx.st, ctx.exchange = st, exchange
         radii = rk.radii_local[:rk.plan.count].clone()
         ctx.mark_non_differentiable(radii)
@@ -327,8 +343,15 @@ class _SparseShardedRasterize(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out_color, grad_radii, grad_depth):
         st, exchange = ctx.st, ctx.exchange
+        if st is None:
+            raise RuntimeError("the sharded rasterizer's backward can run once (its workspace went back to the pool)")
+        _mark("loss")
         acc = sparse_backward_render(st, grad_out_color)
+        _mark("blend backward")
         sparse_return(st, acc)
         exchange.barrier(grad_out_color.device)
+        _mark("return push+barrier")
         grads = sparse_backward_preprocess(st)
+        _mark("gather+preprocess backward")
+        ctx.st = None   # the workspace goes back to the pool now, not when the output tensors die
         return (*grads, None, None, None)
