@@ -78,34 +78,50 @@ __device__ __forceinline__ void tile_rect_rows(float py, int radius, int gy, uin
 }
 
 // ---- owner side, forward -------------------------------------------------------------------------------
-// dest_mask from the records the preprocess kernel wrote (radius in q2.w, centre in q0).
+// dest_mask from the records the preprocess kernel wrote (radius in q2.w, centre in q0), and the per-destination counts
+// of this block of SP_THREADS Gaussians (-> blk_base[block], turned into an exclusive prefix by sparse_scan_kernel).
 __global__ void __launch_bounds__(SP_THREADS)
-sparse_mask_kernel(int n, const SplatRecord* __restrict__ records, int gx, int gy, int world, uint8_t* __restrict__ dest_mask) {
+sparse_mask_kernel(int n, const SplatRecord* __restrict__ records, int gx, int gy, int world, uint8_t* __restrict__ dest_mask,
+                   uint32_t* __restrict__ blk_cnt) {
+  __shared__ uint32_t s_cnt[SP_THREADS / 32][GSR_MAX_PEERS];
   const int idx = blockIdx.x * SP_THREADS + threadIdx.x;
-  if (idx >= n) return;
-  const float4* r = reinterpret_cast<const float4*>(records + idx);
-  const int radius = __float_as_int(__ldg(r + 2).w);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t m = 0;
-  if (radius > 0) {
-    const float4 q0 = __ldg(r);
-    uint32_t ymin, ymax;
-    tile_rect_rows(q0.y, radius, gy, ymin, ymax);
-    const uint32_t xmin = (unsigned)min(gx, max((int)0, (int)((q0.x - radius) / TILE)));
-    const uint32_t xmax = (unsigned)min(gx, max((int)0, (int)((q0.x + radius + TILE - 1) / TILE)));
-    if (xmax > xmin && ymax > ymin) {
-      if (ymax - ymin >= (uint32_t)world) m = (1u << world) - 1u;
-      else
-        for (uint32_t y = ymin; y < ymax; y++) m |= 1u << (y % (uint32_t)world);
+  if (idx < n) {
+    const float4* r = reinterpret_cast<const float4*>(records + idx);
+    const int radius = __float_as_int(__ldg(r + 2).w);
+    if (radius > 0) {
+      const float4 q0 = __ldg(r);
+      uint32_t ymin, ymax;
+      tile_rect_rows(q0.y, radius, gy, ymin, ymax);
+      const uint32_t xmin = (unsigned)min(gx, max((int)0, (int)((q0.x - radius) / TILE)));
+      const uint32_t xmax = (unsigned)min(gx, max((int)0, (int)((q0.x + radius + TILE - 1) / TILE)));
+      if (xmax > xmin && ymax > ymin) {
+        if (ymax - ymin >= (uint32_t)world) m = (1u << world) - 1u;
+        else
+          for (uint32_t y = ymin; y < ymax; y++) m |= 1u << (y % (uint32_t)world);
+      }
     }
+    dest_mask[idx] = (uint8_t)m;
   }
-  dest_mask[idx] = (uint8_t)m;
+#pragma unroll
+  for (int d = 0; d < GSR_MAX_PEERS; d++) {
+    const uint32_t bal = __ballot_sync(0xffffffffu, (m >> d) & 1u);
+    if (lane == 0) s_cnt[warp][d] = __popc(bal);
+  }
+  __syncthreads();
+  if (threadIdx.x < GSR_MAX_PEERS) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < SP_THREADS / 32; w++) c += s_cnt[w][threadIdx.x];
+    blk_cnt[(size_t)blockIdx.x * GSR_MAX_PEERS + threadIdx.x] = c;
+  }
 }
 
-// One CTA: per-block (SP_THREADS Gaussians) per-destination counts, exclusive-scanned over the blocks in index order.
+// One CTA: exclusive scan (over the blocks, in index order) of the per-block per-destination counts, in place.
 constexpr int SCAN_THREADS = 1024;
 __global__ void __launch_bounds__(SCAN_THREADS)
-sparse_scan_kernel(int n, int world, const uint8_t* __restrict__ dest_mask, uint32_t* __restrict__ blk_base,
-                   int32_t* __restrict__ counts) {
+sparse_scan_kernel(int n, int world, uint32_t* __restrict__ blk_base, int32_t* __restrict__ counts) {
   __shared__ uint32_t s_warp[SCAN_THREADS / 32][GSR_MAX_PEERS];
   __shared__ uint32_t s_carry[GSR_MAX_PEERS];
   const int nblocks = (n + SP_THREADS - 1) / SP_THREADS;
@@ -113,27 +129,9 @@ sparse_scan_kernel(int n, int world, const uint8_t* __restrict__ dest_mask, uint
   const int b0 = threadIdx.x * per, b1 = min(nblocks, b0 + per);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto block_counts = [&](int b, uint32_t* c) {
-#pragma unroll
-    for (int d = 0; d < GSR_MAX_PEERS; d++) c[d] = 0;
-    const int first = b * SP_THREADS;
-    if (first + SP_THREADS <= n) {  // the mask array is 256-byte aligned: 128-byte blocks load as 8 x uint4
-      const uint4* p = reinterpret_cast<const uint4*>(dest_mask + first);
-#pragma unroll
-      for (int k = 0; k < SP_THREADS / 16; k++) {
-        const uint4 v = __ldg(p + k);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-#pragma unroll
-          for (int d = 0; d < GSR_MAX_PEERS; d++) c[d] += __popc(w[j] & (0x01010101u << d));
-      }
-    } else {
-      for (int i = first; i < n; i++) {
-        const uint32_t m = dest_mask[i];
-#pragma unroll
-        for (int d = 0; d < GSR_MAX_PEERS; d++) c[d] += (m >> d) & 1u;
-      }
-    }
+    const uint4 v0 = *reinterpret_cast<const uint4*>(blk_base + (size_t)b * GSR_MAX_PEERS);
+    const uint4 v1 = *(reinterpret_cast<const uint4*>(blk_base + (size_t)b * GSR_MAX_PEERS) + 1);
+    c[0] = v0.x; c[1] = v0.y; c[2] = v0.z; c[3] = v0.w; c[4] = v1.x; c[5] = v1.y; c[6] = v1.z; c[7] = v1.w;
   };
   uint32_t mine[GSR_MAX_PEERS];
 #pragma unroll
@@ -420,8 +418,8 @@ int gsr_sparse_preprocess(const gsr_settings* s, const gsr_cloud* shard, const g
     rc = launch_preprocess_fwd(*s, *shard, g, radii_local, st);
     if (rc) return rc;
     const int nblocks = (n + SP_THREADS - 1) / SP_THREADS;
-    sparse_mask_kernel<<<nblocks, SP_THREADS, 0, st>>>(n, g.records, gx, gy, plan->world, sl.dest_mask);
-    sparse_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(n, plan->world, sl.dest_mask, sl.blk_base, counts_row);
+    sparse_mask_kernel<<<nblocks, SP_THREADS, 0, st>>>(n, g.records, gx, gy, plan->world, sl.dest_mask, sl.blk_base);
+    sparse_scan_kernel<<<1, SCAN_THREADS, 0, st>>>(n, plan->world, sl.blk_base, counts_row);
     pa.records = g.records; pa.dest_mask = sl.dest_mask; pa.blk_base = sl.blk_base;
     sparse_push_kernel<<<nblocks, SP_THREADS, 0, st>>>(pa);
     g_launches += 3;
@@ -446,18 +444,19 @@ int gsr_sparse_order(const gsr_settings* s, const gsr_sparse_plan* plan, void* c
   retouch_sparse_kernel<<<(M + 255) / 256, 256, 0, st>>>(plan->world, plan->seg_cap, plan->rank, counts_matrix, sc.g.records,
                                                          gx, gy, radii_cand, sc.g.tiles_touched, sc.g.ident, sc.g.depth_keys,
                                                          v2 ? sc.g.tile_diff : nullptr, tile_diff_copies(gx, gy));
-  if (v2) {
-    TileOwner own; own.stride = plan->world; own.phase = plan->rank;
-    if ((rc = launch_tile_count(sc.g, gx, gy, own, st))) return rc;
-    cudaError_t e2 = cudaMemcpyAsync(host_out, sc.g.R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-    if (e2 != cudaSuccess) return check_cuda(e2, "num_rendered readback");
-  }
-  // the max-count word travels behind num_rendered: host_out[1] (pinned), written through a device word in the workspace
-  int32_t* dev_word = reinterpret_cast<int32_t*>(sc.g.depth_keys_sorted);  // overwritten by the sort afterwards: read first
+  // host_out[1] (largest segment anywhere) is copied out BEFORE host_out[0] (num_rendered): a host that polls word 0
+  // finds word 1 already in place. The device word is overwritten by the sort afterwards: read first.
+  int32_t* dev_word = reinterpret_cast<int32_t*>(sc.g.depth_keys_sorted);
   sparse_max_count_kernel<<<1, 32, 0, st>>>(plan->world, counts_matrix, dev_word);
   g_launches += 2;
   cudaError_t e = cudaMemcpyAsync(host_out + 1, dev_word, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return check_cuda(e, "max-count readback");
+  if (v2) {
+    TileOwner own; own.stride = plan->world; own.phase = plan->rank;
+    if ((rc = launch_tile_count(sc.g, gx, gy, own, st))) return rc;
+    e = cudaMemcpyAsync(host_out, sc.g.R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return check_cuda(e, "num_rendered readback");
+  }
   gsr_cloud c{};
   c.P = M;
   return run_depth_order_and_scan(c, sc.g, v2 ? nullptr : host_out, st, s->debug != 0);

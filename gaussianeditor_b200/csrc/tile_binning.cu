@@ -254,8 +254,8 @@ struct SortArgs {
   const uint32_t* digit_base;   // [NB] exclusive scan of this pass's global digit histogram
 };
 
-template <bool EMIT>
-__global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const SortArgs a) {
+template <bool EMIT, int NBITS>
+__global__ void __launch_bounds__(SORT_THREADS, 4) tile_sort_pass_kernel(const SortArgs a) {
   __shared__ uint32_t s_whist[SORT_WARPS][NB];
   __shared__ uint32_t s_off[NB];    // CTA-exclusive prefix over the digits, later the global offset of the digit's run
   __shared__ uint32_t s_wsum[SORT_WARPS];
@@ -274,11 +274,13 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
   const uint32_t tile_base = tile * (uint32_t)SORT_TILE;
   if (tile_base >= R) return;  // CTA-uniform
   const uint32_t nvalid = min((uint32_t)SORT_TILE, R - tile_base);
-  const uint32_t dmask = (1u << a.nbits) - 1u;
+  constexpr uint32_t dmask = (1u << NBITS) - 1u;  // digit width is a template parameter: the ranking below is straight-line code
   uint32_t* whist = s_whist[warp];
 
-  uint16_t key[SORT_ITEMS];
-  uint32_t val[SORT_ITEMS], rank[SORT_ITEMS];
+  // Register diet (64 registers -> 4 CTAs per SM): one word per item = key (low 16 bits) | rank of its digit inside the
+  // warp (high 16 bits, < 512); the values are not held at all until the reorder step -- pass 1 leaves them in shared
+  // memory where the transposition put them, pass 2 loads them then.
+  uint32_t kr[SORT_ITEMS];
   const uint32_t s_begin = tile_base + (uint32_t)warp * (32u * SORT_ITEMS);  // first slot of this warp
 
   if (EMIT) {
@@ -297,23 +299,27 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
         n = min(stride, n - j * stride);
       }
       const int r_lo = lo;
-      uint32_t* soff = s_vals + warp * (32 * SORT_ITEMS);
-      uint16_t* skey = s_keys + warp * (32 * SORT_ITEMS);
+      uint32_t* sval = s_vals + warp * (32 * SORT_ITEMS);   // this warp's 512 values (swizzled, warp-striped)
+      uint16_t* skey = s_keys + warp * (32 * SORT_ITEMS);   // first the staged offsets, then this warp's 512 keys
+      // offsets relative to the warp's first slot, saturated to 16 bits: only "<= slot" with slot - s_begin < 512 is
+      // ever asked of them, so 512 of them fit the warp's key area and the value area stays free for the results
 #pragma unroll
-      for (int i = 0; i < SORT_ITEMS; i++) soff[i * 32 + lane] = __ldg(a.offsets + min(r_lo + i * 32 + lane, a.P - 1));
+      for (int i = 0; i < SORT_ITEMS; i++)
+        skey[i * 32 + lane] = (uint16_t)min(__ldg(a.offsets + min(r_lo + i * 32 + lane, a.P - 1)) - s_begin, 0xFFFFu);
       __syncwarp();
       // BLOCKED generation: lane l walks the 16 consecutive slots s_begin + 16 l ... -- one binary search for its first
       // slot, then tile ids by incrementing (column, row) inside the Gaussian's rectangle; a new Gaussian is fetched
       // only when the walk crosses the end of the current one (every visible rank owns >= 1 slot: one step).
-      const uint32_t first = s_begin + (uint32_t)(SORT_ITEMS * lane);
-      const uint32_t sc = min(first, R - 1);
-      int j = 0;  // smallest j with soff[j] > sc
+      const uint32_t first = (uint32_t)(SORT_ITEMS * lane);           // relative to s_begin
+      const uint32_t last_rel = R - 1 - s_begin;                       // last valid slot, relative
+      const uint32_t sc = min(first, last_rel);
+      int j = 0;  // smallest j with skey[j] > sc
 #pragma unroll
       for (int step = 256; step > 0; step >>= 1)
-        if (soff[j + step - 1] <= sc) j += step;
+        if ((uint32_t)skey[j + step - 1] <= sc) j += step;
       uint32_t idx, end, w, xmin, ybase, rx, ry;
       auto fetch = [&](int jj) {
-        end = soff[jj];
+        end = skey[jj];
         idx = __ldg(a.order + min(r_lo + jj, a.P - 1));
         const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.records + idx));
         uint2 rmin, rmax;
@@ -326,72 +332,65 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
       };
       fetch(j);
       {
-        const uint32_t k = sc - (end - __ldg(a.tiles_touched + idx));
+        // absolute arithmetic for the position inside the first Gaussian (its start may lie before s_begin)
+        const uint32_t end_abs = __ldg(a.offsets + min(r_lo + j, a.P - 1));
+        const uint32_t k = (s_begin + sc) - (end_abs - __ldg(a.tiles_touched + idx));
         ry = k / w;
         rx = k - ry * w;
       }
-      uint16_t bkey[SORT_ITEMS];
-      uint32_t bval[SORT_ITEMS];
+      uint32_t bk[SORT_ITEMS / 2];  // two 16-bit keys per register
 #pragma unroll
       for (int i = 0; i < SORT_ITEMS; i++) {
         const uint32_t sl = first + i;
-        if (sl < R && sl >= end) {  // crossed into the next depth rank
+        if (sl <= last_rel && sl >= end) {  // crossed into the next depth rank
           j++;
           fetch(j);
           rx = 0; ry = 0;
         }
-        bkey[i] = (uint16_t)((ybase + ry * (uint32_t)a.own_stride) * a.gx + (xmin + rx));
-        bval[i] = idx;
+        const uint32_t kk = ((ybase + ry * (uint32_t)a.own_stride) * a.gx + (xmin + rx)) & 0xFFFFu;
+        if (i & 1) bk[i >> 1] |= kk << 16; else bk[i >> 1] = kk;
+        // blocked -> warp-striped through shared memory (the stable ranking below needs item i of lane l to be slot
+        // 32 i + l); the XOR swizzle makes both the writes (stride 16) and the reads (stride 1) bank-conflict free
+        const int pl = SORT_ITEMS * lane + i;
+        sval[pl ^ ((pl >> 5) & 15)] = idx;
         rx++;
         if (rx == w) { rx = 0; ry++; }
       }
-      __syncwarp();  // everybody is done with the staged offsets: their shared memory now carries the transposition
-      // blocked -> warp-striped (the stable ranking below needs item i of lane l to be slot 32 i + l); the XOR swizzle
-      // makes both the writes (stride 16) and the reads (stride 1) bank-conflict free
+      __syncwarp();  // everybody is done with the staged offsets: the key area now takes the keys
 #pragma unroll
       for (int i = 0; i < SORT_ITEMS; i++) {
         const int pl = SORT_ITEMS * lane + i;
-        const int ph = pl ^ ((pl >> 5) & 15);
-        soff[ph] = bval[i];
-        skey[ph] = bkey[i];
+        skey[pl ^ ((pl >> 5) & 15)] = (uint16_t)(bk[i >> 1] >> (16 * (i & 1)));
       }
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < SORT_ITEMS; i++) {
         const int pl = 32 * i + lane;
-        const int ph = pl ^ ((pl >> 5) & 15);
-        val[i] = soff[ph];
-        key[i] = skey[ph];
+        kr[i] = skey[pl ^ ((pl >> 5) & 15)];
       }
     } else {
 #pragma unroll
-      for (int i = 0; i < SORT_ITEMS; i++) { key[i] = 0; val[i] = 0; }
+      for (int i = 0; i < SORT_ITEMS; i++) kr[i] = 0;
     }
   } else {
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; i++) {
       const uint32_t e = s_begin + 32u * i + lane;
-      key[i] = 0; val[i] = 0;
-      if (e < R) {
-        key[i] = a.keys_in[e];
-        val[i] = a.vals_in[e];
-      }
+      kr[i] = e < R ? (uint32_t)a.keys_in[e] : 0u;
     }
   }
   // ---- stable rank of every item's digit among the warp's earlier slots (match_any + per-warp counters) ----
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const bool valid = s_begin + 32u * i + lane < R;
-    const uint32_t d = valid ? (((uint32_t)key[i] >> a.shift) & dmask) : 0xFFFFFFFFu;
+    const uint32_t d = valid ? ((kr[i] >> a.shift) & dmask) : 0xFFFFFFFFu;
     // lanes with the same digit: one ballot per digit bit (MATCH.ANY measured ~100 cycles of SM time per warp
     // instruction here: 16 of them per thread were 40 % of this kernel's stall samples)
     uint32_t peers = __ballot_sync(F, valid);
 #pragma unroll
-    for (int b = 0; b < 8; b++) {
-      if (b < a.nbits) {  // warp-uniform
-        const uint32_t bal = __ballot_sync(F, (d >> b) & 1u);
-        peers &= ((d >> b) & 1u) ? bal : ~bal;
-      }
+    for (int b = 0; b < NBITS; b++) {
+      const uint32_t bal = __ballot_sync(F, (d >> b) & 1u);
+      peers &= ((d >> b) & 1u) ? bal : ~bal;
     }
     const uint32_t lt = peers & ((1u << lane) - 1u);
     uint32_t prev = 0;
@@ -399,7 +398,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
     __syncwarp();
     if (valid && lt == 0) whist[d] = prev + __popc(peers);
     __syncwarp();
-    rank[i] = prev + __popc(lt);
+    kr[i] |= (prev + __popc(lt)) << 16;
   }
   __syncthreads();
 
@@ -432,15 +431,28 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
   s_off[tid] = cta_excl;
   __syncthreads();
 
-  // ---- reorder inside the CTA (before the look-back: it frees the key / value / rank registers) ----
+  // ---- reorder inside the CTA (before the look-back: it frees the registers) ----
+  {
+    uint32_t v[SORT_ITEMS];
+    const uint32_t* sval_w = s_vals + warp * (32 * SORT_ITEMS);
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++) {
-    const uint32_t e = s_begin + 32u * i + lane;
-    if (e < R) {
-      const uint32_t d = ((uint32_t)key[i] >> a.shift) & dmask;
-      const uint32_t pos = s_off[d] + s_whist[warp][d] + rank[i];
-      s_keys[pos] = key[i];
-      s_vals[pos] = val[i];
+    for (int i = 0; i < SORT_ITEMS; i++) {
+      const uint32_t e = s_begin + 32u * i + lane;
+      const int pl = 32 * i + lane;
+      v[i] = 0;
+      if (e < R) v[i] = EMIT ? sval_w[pl ^ ((pl >> 5) & 15)] : a.vals_in[e];
+    }
+    __syncthreads();  // pass 1: every value has left the staging area before it is overwritten
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; i++) {
+      const uint32_t e = s_begin + 32u * i + lane;
+      if (e < R) {
+        const uint32_t k = kr[i] & 0xFFFFu;
+        const uint32_t d = (k >> a.shift) & dmask;
+        const uint32_t pos = s_off[d] + s_whist[warp][d] + (kr[i] >> 16);
+        s_keys[pos] = (uint16_t)k;
+        s_vals[pos] = v[i];
+      }
     }
   }
   __syncthreads();
@@ -456,7 +468,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
       // of them is inspected. The "inclusive" front can only advance LB_WINDOW tiles per L2 round trip (a tile that
       // sees nothing but aggregates in its window has to go one window further back), and with ~1600 tiles of a few
       // microseconds each that chain, not the sorting work, was the critical path (measured: 8 -> 0.34 us per round).
-      constexpr int LB_WINDOW = 32;
+      constexpr int LB_WINDOW = 16;
       bool done = false;
       for (int p = (int)tile - 1; !done && p >= 0; p -= LB_WINDOW) {
         uint32_t v[LB_WINDOW];
@@ -486,6 +498,20 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) tile_sort_pass_kernel(const S
     const uint32_t out = s_off[d] + p;
     a.keys_out[out] = k;
     a.vals_out[out] = s_vals[p];
+  }
+}
+
+template <bool EMIT>
+void launch_pass(int nbits, int ntiles, const SortArgs& a, cudaStream_t st) {
+  switch (nbits) {
+    case 1: tile_sort_pass_kernel<EMIT, 1><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
+    case 2: tile_sort_pass_kernel<EMIT, 2><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
+    case 3: tile_sort_pass_kernel<EMIT, 3><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
+    case 4: tile_sort_pass_kernel<EMIT, 4><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
+    case 5: tile_sort_pass_kernel<EMIT, 5><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
+    case 6: tile_sort_pass_kernel<EMIT, 6><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
+    case 7: tile_sort_pass_kernel<EMIT, 7><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
+    default: tile_sort_pass_kernel<EMIT, 8><<<ntiles, SORT_THREADS, 0, st>>>(a); break;
   }
 }
 
@@ -545,7 +571,7 @@ int run_tile_binning(const gsr_settings& s, int P, int R, bool speculative, cons
   a.keys_out = reinterpret_cast<uint16_t*>(b.keys_unsorted); a.vals_out = b.vals_unsorted;
   a.shift = 0; a.nbits = bits1;
   a.ticket = ticket; a.state = state; a.digit_base = digit_base;
-  tile_sort_pass_kernel<true><<<ntiles, SORT_THREADS, 0, st>>>(a);
+  launch_pass<true>(a.nbits, ntiles, a, st);
   g_launches++;
   int rc = check_launch("tile_sort_pass1", debug, st);
   if (rc) return rc;
@@ -558,7 +584,7 @@ int run_tile_binning(const gsr_settings& s, int P, int R, bool speculative, cons
   a.keys_out = reinterpret_cast<uint16_t*>(b.keys_sorted); a.vals_out = b.point_list;
   a.shift = bits1; a.nbits = bits2;
   a.ticket = ticket + 1; a.state = state + (size_t)(ntiles > 0 ? ntiles : 1) * NB; a.digit_base = digit_base + NB;
-  tile_sort_pass_kernel<false><<<ntiles, SORT_THREADS, 0, st>>>(a);
+  launch_pass<false>(a.nbits, ntiles, a, st);
   g_launches++;
   return check_launch("tile_sort_pass2", debug, st);
 }

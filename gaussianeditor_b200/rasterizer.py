@@ -43,6 +43,7 @@ _size_cache: dict = {}
 _pinned: dict = {}
 _r_hint: dict = {}          # (device, P, W, H) -> largest num_rendered seen recently
 SPECULATIVE = True          # launch the second forward half before num_rendered is known (see _forward_impl)
+SPEC_STATS = {"launched": 0, "missed": 0}   # speculative second halves launched / redone because the guess was too small
 
 
 def _f32c(t: torch.Tensor, device) -> torch.Tensor:
@@ -182,8 +183,11 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
                                                           _ptr(state.radii), _ptr(color), _ptr(depth), st),
                        "gsr_forward_render_speculative")
             R = _wait_count(pinned, ev.synchronize)
+            SPEC_STATS["launched"] += 1
             if R <= cap:
                 state.num_rendered, state.cap, done = R, cap, True
+            else:
+                SPEC_STATS["missed"] += 1
         if not done:
             R = _wait_count(pinned, stream.synchronize)
             state.num_rendered = state.cap = R

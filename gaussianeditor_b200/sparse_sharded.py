@@ -30,7 +30,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .rasterizer import GaussianRasterizationSettings, _f32c, _make_cloud, _make_settings, _ptr
+from .rasterizer import GaussianRasterizationSettings, _f32c, _make_cloud, _make_settings, _ptr, _wait_count
 from .sharded import ACC_STRIDE, Exchange, PeerWorkspace, ShardPlan, shard_slice
 
 MAXP = 8  # GSR_MAX_PEERS
@@ -164,11 +164,12 @@ def sparse_order(st: SparseStep):
         st.radii_cand = rk.get("radii_cand", M, torch.int32, grow=1.25)
         stream = torch.cuda.current_stream(rk.device)
         cand_bytes = lib.gsr_sparse_candidate_bytes(rk.plan.world, st.cap)
+        rk.pinned[0] = -1   # both words are copied out BEFORE the depth sort is queued: the host gets them early
         _lib.check(lib.gsr_sparse_order(C.byref(st.s), C.byref(st.cplan), _ptr(rk.cand), cand_bytes, _ptr(rk.matrix),
                                         _ptr(st.radii_cand), C.c_void_p(rk.pinned.data_ptr()),
                                         C.c_void_p(stream.cuda_stream)), "gsr_sparse_order")
-        stream.synchronize()
-        st.R, st.max_count = int(rk.pinned[0]), int(rk.pinned[1])
+        st.R = _wait_count(rk.pinned, stream.synchronize)   # the max-count word was copied just before it
+        st.max_count = int(rk.pinned[1])
     return st.R, st.max_count
 
 
