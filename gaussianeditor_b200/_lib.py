@@ -25,9 +25,9 @@ SYMBOLS = [
     "gsr_shard_backward_preprocess",
     "gsr_peer_alloc", "gsr_peer_open", "gsr_peer_close", "gsr_peer_free", "gsr_shard_preprocess_p2p",
     "gsr_forward_preprocess_raw", "gsr_backward_raw",
-    "gsr_alpha_image", "gsr_backward_alpha",
+    "gsr_alpha_image", "gsr_backward_alpha", "gsr_camera_scratch_bytes", "gsr_backward_camera",
     "gsr_sparse_local_bytes", "gsr_sparse_candidate_bytes", "gsr_sparse_view", "gsr_sparse_preprocess", "gsr_sparse_order",
-    "gsr_sparse_return", "gsr_sparse_backward_preprocess", "gsr_frame_broadcast",
+    "gsr_sparse_return", "gsr_sparse_backward_preprocess", "gsr_frame_broadcast", "gsr_peer_barrier",
 ]
 
 
@@ -54,6 +54,11 @@ class Grads(C.Structure):
         ("dL_dopacity", C.c_void_p), ("dL_dcov3D", C.c_void_p), ("dL_dsh", C.c_void_p),
         ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
     ]
+
+
+class CameraGrads(C.Structure):
+    _fields_ = [("dL_dviewmatrix", C.c_void_p), ("dL_dprojmatrix", C.c_void_p), ("dL_dcampos", C.c_void_p),
+                ("scratch", C.c_void_p), ("scratch_bytes", C.c_size_t)]
 
 
 class GeometryView(C.Structure):
@@ -137,6 +142,10 @@ def load():
     lib.gsr_backward_alpha.restype = C.c_int
     lib.gsr_backward_alpha.argtypes = [C.POINTER(Settings), C.POINTER(Cloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp,
                                        sz, C.POINTER(Grads), vp]
+    lib.gsr_camera_scratch_bytes.restype = sz; lib.gsr_camera_scratch_bytes.argtypes = [i32]
+    lib.gsr_backward_camera.restype = C.c_int
+    lib.gsr_backward_camera.argtypes = [C.POINTER(Settings), C.POINTER(Cloud), i32, vp, sz, vp, sz, vp, sz, vp, vp, vp, vp,
+                                        sz, C.POINTER(Grads), C.POINTER(CameraGrads), vp]
     lib.gsr_alpha_image.restype = C.c_int
     lib.gsr_alpha_image.argtypes = [vp, sz, i32, i32, vp, vp]
     lib.gsr_mark_visible.restype = C.c_int
@@ -192,6 +201,8 @@ def load():
     lib.gsr_sparse_return.argtypes = [SP, vp, vp, C.POINTER(vp), vp]
     lib.gsr_sparse_backward_preprocess.restype = C.c_int
     lib.gsr_sparse_backward_preprocess.argtypes = [S, Cl, SP, vp, sz, vp, vp, sz, vp, sz, C.POINTER(Grads), vp]
+    lib.gsr_peer_barrier.restype = C.c_int
+    lib.gsr_peer_barrier.argtypes = [i32, i32, C.POINTER(vp), C.c_uint32, i32, vp]
     lib.gsr_frame_broadcast.restype = C.c_int
     lib.gsr_frame_broadcast.argtypes = [TO, i32, i32, vp, C.POINTER(vp), vp]
     if lib.gsr_abi_version() != 2:

@@ -198,7 +198,7 @@ int gsr_forward_render_speculative(const gsr_settings* s, const gsr_cloud* c, in
 static int backward_impl(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
                          const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
                          const int32_t* radii, const float* dL_dout_color, const float* dL_dout_alpha, void* scratch,
-                         size_t scratch_bytes, const gsr_grads* gr, void* stream) {
+                         size_t scratch_bytes, const gsr_grads* gr, void* stream, const gsr_camera_grads* cam = nullptr) {
   int rc = validate_cloud(s, c);
   if (rc) return rc;
   if (!gr || !dL_dout_color) { set_error("grads / dL_dout_color is null"); return GSR_ERR_INVALID; }
@@ -226,7 +226,35 @@ static int backward_impl(const gsr_settings* s, const gsr_cloud* c, int32_t R, c
     }
   }
   StageScope t(ST_PRE_BWD, st);
+  if (cam) {
+    if (!cam->dL_dviewmatrix || !cam->dL_dprojmatrix || !cam->dL_dcampos || !cam->scratch ||
+        cam->scratch_bytes < camera_scratch_bytes(c->P)) {
+      set_error("camera gradients: null output or scratch smaller than gsr_camera_scratch_bytes(P)");
+      return GSR_ERR_INVALID;
+    }
+    CameraBackward cb{cam->dL_dviewmatrix, cam->dL_dprojmatrix, cam->dL_dcampos, (float*)cam->scratch};
+    return launch_preprocess_bwd(*s, *c, g, radii, (const float*)scratch, *gr, st, nullptr, &cb);
+  }
   return launch_preprocess_bwd(*s, *c, g, radii, (const float*)scratch, *gr, st);
+}
+
+size_t gsr_camera_scratch_bytes(int32_t P) { return camera_scratch_bytes(P > 0 ? P : 1); }
+
+int gsr_backward_camera(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,
+                        const void* binning, size_t binning_bytes, const void* image, size_t image_bytes,
+                        const int32_t* radii, const float* dL_dout_color, const float* dL_dout_alpha, void* scratch,
+                        size_t scratch_bytes, const gsr_grads* gr, const gsr_camera_grads* cam, void* stream) {
+  if (!cam) { set_error("camera gradients: null struct"); return GSR_ERR_INVALID; }
+  if (c && c->P == 0) {  // nothing contributes: the gradients are zero
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaSuccess;
+    if (cam->dL_dviewmatrix) e = cudaMemsetAsync(cam->dL_dviewmatrix, 0, 64, st);
+    if (e == cudaSuccess && cam->dL_dprojmatrix) e = cudaMemsetAsync(cam->dL_dprojmatrix, 0, 64, st);
+    if (e == cudaSuccess && cam->dL_dcampos) e = cudaMemsetAsync(cam->dL_dcampos, 0, 12, st);
+    if (e != cudaSuccess) return check_cuda(e, "camera gradient memset");
+  }
+  return backward_impl(s, c, R, geometry, geometry_bytes, binning, binning_bytes, image, image_bytes, radii,
+                       dL_dout_color, dL_dout_alpha, scratch, scratch_bytes, gr, stream, cam);
 }
 
 int gsr_backward(const gsr_settings* s, const gsr_cloud* c, int32_t R, const void* geometry, size_t geometry_bytes,

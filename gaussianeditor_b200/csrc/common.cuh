@@ -150,8 +150,17 @@ struct RawBackward {
   const float* features_rest;
   float* dL_dfeatures_rest;
 };
+// cam != nullptr: also dL/dviewmatrix [16], dL/dprojmatrix [16], dL/dcampos [3] (opt-in; scratch = camera_scratch_bytes(P))
+struct CameraBackward {
+  float* dL_dviewmatrix;
+  float* dL_dprojmatrix;
+  float* dL_dcampos;
+  float* scratch;
+};
+size_t camera_scratch_bytes(int P);
 int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
-                          const float* acc, const gsr_grads& gr, cudaStream_t st, const RawBackward* raw = nullptr);
+                          const float* acc, const gsr_grads& gr, cudaStream_t st, const RawBackward* raw = nullptr,
+                          const CameraBackward* cam = nullptr);
 // out_alpha[i] = 1 - final_T[i]  (the reference keeps final_T as ImageState::accum_alpha, rasterizer_impl.h:50)
 int launch_alpha_image(const float* final_T, size_t n, float* out_alpha, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present, cudaStream_t st);

@@ -71,6 +71,7 @@ struct PbArgs {
   const float* opacities;
   const float* features_rest;
   float* dL_dfeatures_rest;
+  float* cam_partial;  // CAM variant: [nblocks, CAM_STRIDE] block partial sums of the camera gradients
 };
 
 __device__ __forceinline__ M3 quat_to_R(float r, float x, float y, float z) {
@@ -81,9 +82,23 @@ __device__ __forceinline__ M3 quat_to_R(float r, float x, float y, float z) {
   return R;
 }
 
-template <bool BULK, bool RAW = false>
+// Camera gradients (opt-in, gsr_backward_camera; the reference has none: its autograd returns None for the settings,
+// diff_gaussian_rasterization/__init__.py:213-223). viewmatrix, projmatrix and campos are treated as INDEPENDENT inputs,
+// exactly as the forward reads them; a caller that builds projmatrix / campos from the view matrix chains the three.
+// Compact per-thread accumulator layout, CAM_N floats:
+//   [4k + j]      dL/dview[k + 4j]   k = 0..2 (row of t = view * mean), j = 0..3 (x, y, z, 1)
+//   [12 + 4r + j] dL/dproj[i + 4j]   i = (0, 1, 3)[r] (p_hom.x, .y, .w)
+//   [24 + c]      dL/dcampos[c]
+constexpr int CAM_N = 27, CAM_STRIDE = 32;
+
+template <bool BULK, bool RAW = false, bool CAM = false>
 __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs a) {
   static_assert(!(BULK && RAW), "the RAW variant stages its SH block itself");
+  float cg[CAM ? CAM_N : 1];
+  if (CAM) {
+#pragma unroll
+    for (int i = 0; i < CAM_N; i++) cg[i] = 0.f;
+  }
   __shared__ __align__(16) float rows[BULK ? PB_THREADS * ROW_WORDS : 4];
   // RAW: the CTA's features_rest rows in (one bulk load), overwritten in place by their gradients, out (one bulk store)
   __shared__ __align__(128) float s_rest[RAW ? PB_THREADS * 45 : 1];
@@ -240,6 +255,25 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
       dmean[0] = vm[0] * dL_dtx + vm[1] * dL_dty + vm[2] * dL_dtz;
       dmean[1] = vm[4] * dL_dtx + vm[5] * dL_dty + vm[6] * dL_dtz;
       dmean[2] = vm[8] * dL_dtx + vm[9] * dL_dty + vm[10] * dL_dtz;
+      if (CAM) {
+        // through t = view * mean (same dL/dt, same clamp convention as the mean gradient above)
+        const float dt[3] = {dL_dtx, dL_dty, dL_dtz};
+        const float mj[4] = {mean.x, mean.y, mean.z, 1.0f};
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) cg[4 * k + j] += dt[k] * mj[j];
+        // through W (the rotation part of view) in T = W * J:  T[0][r] = W[0][r] J00 + W[2][r] J02,
+        // T[1][r] = W[1][r] J11 + W[2][r] J12  with W[0] = (v0,v4,v8), W[1] = (v1,v5,v9), W[2] = (v2,v6,v10)
+        const float J00 = J.m[0][0], J02 = J.m[0][2], J11 = J.m[1][1], J12 = J.m[1][2];
+        const float dT0[3] = {dL_dT00, dL_dT01, dL_dT02}, dT1[3] = {dL_dT10, dL_dT11, dL_dT12};
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+          cg[4 * 0 + r] += dT0[r] * J00;                    // view[0 + 4r]
+          cg[4 * 1 + r] += dT1[r] * J11;                    // view[1 + 4r]
+          cg[4 * 2 + r] += dT0[r] * J02 + dT1[r] * J12;     // view[2 + 4r]
+        }
+      }
     }
 
     // ---- projection term (backward.cu:372-387) ----
@@ -253,6 +287,15 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
       dmean[0] += (proj[0] * m_w - proj[3] * mul1) * g2x + (proj[1] * m_w - proj[3] * mul2) * g2y;
       dmean[1] += (proj[4] * m_w - proj[7] * mul1) * g2x + (proj[5] * m_w - proj[7] * mul2) * g2y;
       dmean[2] += (proj[8] * m_w - proj[11] * mul1) * g2x + (proj[9] * m_w - proj[11] * mul2) * g2y;
+      if (CAM) {
+        // p_proj = p_hom.xy / (p_hom.w + eps): dL/dp_hom.x = g2x m_w, .y = g2y m_w, .w = -(g2x hx + g2y hy) m_w^2
+        const float dh[3] = {g2x * m_w, g2y * m_w, -(g2x * mul1 + g2y * mul2)};
+        const float mj[4] = {mean.x, mean.y, mean.z, 1.0f};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int j = 0; j < 4; j++) cg[12 + 4 * r + j] += dh[r] * mj[j];
+      }
     }
 
     // ---- 3-D covariance -> scale / rotation (backward.cu:278-341) ----
@@ -404,6 +447,11 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
       dmean[0] += ((+sum2 - dir_orig.x * dir_orig.x) * ddir[0] - dir_orig.y * dir_orig.x * ddir[1] - dir_orig.z * dir_orig.x * ddir[2]) * invsum32;
       dmean[1] += (-dir_orig.x * dir_orig.y * ddir[0] + (sum2 - dir_orig.y * dir_orig.y) * ddir[1] - dir_orig.z * dir_orig.y * ddir[2]) * invsum32;
       dmean[2] += (-dir_orig.x * dir_orig.z * ddir[0] - dir_orig.y * dir_orig.z * ddir[1] + (sum2 - dir_orig.z * dir_orig.z) * ddir[2]) * invsum32;
+      if (CAM) {  // dir = mean - campos: the camera position receives minus what the mean receives through the SH direction
+        cg[24] -= ((+sum2 - dir_orig.x * dir_orig.x) * ddir[0] - dir_orig.y * dir_orig.x * ddir[1] - dir_orig.z * dir_orig.x * ddir[2]) * invsum32;
+        cg[25] -= (-dir_orig.x * dir_orig.y * ddir[0] + (sum2 - dir_orig.y * dir_orig.y) * ddir[1] - dir_orig.z * dir_orig.y * ddir[2]) * invsum32;
+        cg[26] -= (-dir_orig.x * dir_orig.z * ddir[0] - dir_orig.y * dir_orig.z * ddir[1] + (sum2 - dir_orig.z * dir_orig.z) * ddir[2]) * invsum32;
+      }
     }
     if (BULK) {
       fence_proxy_async_smem();
@@ -448,13 +496,58 @@ __global__ void __launch_bounds__(PB_THREADS) preprocess_bwd_kernel(const PbArgs
     }
   }
   if (BULK) bulk_wait_read0();  // the row must stay valid until the TMA store has read it
+  if (CAM) {
+    // block partial sums -> cam_partial[block, CAM_STRIDE]; camera_reduce_kernel adds the blocks up (two stages instead
+    // of 27 same-address atomics per block)
+    __shared__ float s_cam[PB_THREADS / 32][CAM_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < CAM_N; i++) {
+      float v = cg[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) s_cam[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < CAM_STRIDE) {
+      float v = 0.f;
+      if (threadIdx.x < CAM_N)
+#pragma unroll
+        for (int w = 0; w < PB_THREADS / 32; w++) v += s_cam[w][threadIdx.x];
+      a.cam_partial[(size_t)blockIdx.x * CAM_STRIDE + threadIdx.x] = v;
+    }
+  }
+}
+
+// sums the per-block partials and scatters the compact layout into dL/dviewmatrix[16], dL/dprojmatrix[16], dL/dcampos[3]
+__global__ void __launch_bounds__(1024) camera_reduce_kernel(const float* __restrict__ partial, int nblocks, float* __restrict__ dview,
+                                                             float* __restrict__ dproj, float* __restrict__ dcampos) {
+  __shared__ float s[32][CAM_STRIDE + 1];
+  const int c = threadIdx.x & 31, r = threadIdx.x >> 5;
+  float v = 0.f;
+  for (int b = r; b < nblocks; b += 32) v += partial[(size_t)b * CAM_STRIDE + c];
+  s[r][c] = v;
+  __syncthreads();
+  if (threadIdx.x < 16) { dview[threadIdx.x] = 0.f; dproj[threadIdx.x] = 0.f; }
+  __syncthreads();
+  if (r == 0 && c < CAM_N) {
+    float t = 0.f;
+    for (int k = 0; k < 32; k++) t += s[k][c];
+    if (c < 12) dview[(c >> 2) + 4 * (c & 3)] = t;
+    else if (c < 24) { const int rr = (c - 12) >> 2, j = (c - 12) & 3; dproj[(rr == 2 ? 3 : rr) + 4 * j] = t; }
+    else dcampos[c - 24] = t;
+  }
 }
 
 }  // namespace
 
+size_t camera_scratch_bytes(int P) { return align_up((size_t)((P + PB_THREADS - 1) / PB_THREADS + 1) * CAM_STRIDE * sizeof(float)); }
+
 int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, const int32_t* radii,
-                          const float* acc, const gsr_grads& gr, cudaStream_t st, const RawBackward* raw) {
+                          const float* acc, const gsr_grads& gr, cudaStream_t st, const RawBackward* raw,
+                          const CameraBackward* cam) {
   PbArgs a;
+  a.cam_partial = cam ? cam->scratch : nullptr;
   a.opacities = c.opacities;
   a.features_rest = raw ? raw->features_rest : nullptr;
   a.dL_dfeatures_rest = raw ? raw->dL_dfeatures_rest : nullptr;
@@ -473,6 +566,16 @@ int launch_preprocess_bwd(const gsr_settings& s, const gsr_cloud& c, const Geome
   const bool bulk = g_opt.preprocess_variant >= 1 && c.shs != nullptr && gr.dL_dsh != nullptr &&
                     (s.sh_coeffs * 12) % 16 == 0 && s.sh_coeffs * 12 <= 192 &&
                     (reinterpret_cast<uintptr_t>(c.shs) % 16) == 0 && (reinterpret_cast<uintptr_t>(gr.dL_dsh) % 16) == 0;
+  if (cam) {  // opt-in camera gradients (never together with the RAW entry point)
+    if (raw) { set_error("camera gradients are not available on the fused-activation entry point"); return GSR_ERR_INVALID; }
+    if (bulk)
+      preprocess_bwd_kernel<true, false, true><<<grid, PB_THREADS, 0, st>>>(a);
+    else
+      preprocess_bwd_kernel<false, false, true><<<grid, PB_THREADS, 0, st>>>(a);
+    camera_reduce_kernel<<<1, 1024, 0, st>>>(cam->scratch, grid, cam->dL_dviewmatrix, cam->dL_dprojmatrix, cam->dL_dcampos);
+    g_launches += 2;
+    return check_launch("preprocess_bwd (camera)", s.debug != 0, st);
+  }
   if (raw)
     preprocess_bwd_kernel<false, true><<<grid, PB_THREADS, 0, st>>>(a);
   else if (bulk)

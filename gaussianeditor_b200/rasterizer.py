@@ -206,7 +206,11 @@ def _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations, cov
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings, return_alpha=False):
+                        raster_settings, return_alpha=False, camera_grad=False):
+    if camera_grad:   # the camera arrays become autograd inputs of the node (they are read from the settings as usual)
+        rs = raster_settings
+        return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                         cov3Ds_precomp, rs, return_alpha, rs.viewmatrix, rs.projmatrix, rs.campos)
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, raster_settings, return_alpha)
 
@@ -224,10 +228,12 @@ def _alpha_image(lib, state, device):
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                raster_settings, return_alpha=False):
+                raster_settings, return_alpha=False, viewmatrix=None, projmatrix=None, campos=None):
         color, depth, state, inputs = _forward_impl(means3D, sh, colors_precomp, opacities, scales, rotations,
                                                     cov3Ds_precomp, raster_settings)
         ctx.raster_settings = raster_settings
+        ctx.camera_grad = viewmatrix is not None
+        ctx.n_inputs = 10 + (3 if ctx.camera_grad else 0)
         ctx.state = state
         ctx.save_for_backward(*inputs, state.radii, state.geom, state.binning, state.img)
         ctx.mark_non_differentiable(state.radii)
@@ -262,7 +268,19 @@ class _RasterizeGaussians(torch.autograd.Function):
                 gr = _lib.Grads(_ptr(dL_dmeans3D), _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dopacity),
                                 _ptr(dL_dcov3D), _ptr(dL_dsh), _ptr(dL_dscales), _ptr(dL_drotations))
                 st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-                if grad_alpha is not None:
+                if ctx.camera_grad:
+                    d_view = torch.empty(16, **f32); d_proj = torch.empty(16, **f32); d_cam = torch.empty(3, **f32)
+                    cbytes = lib.gsr_camera_scratch_bytes(P)
+                    cscratch = torch.empty(cbytes, dtype=torch.uint8, device=device)
+                    cam = _lib.CameraGrads(_ptr(d_view), _ptr(d_proj), _ptr(d_cam), _ptr(cscratch), cbytes)
+                    ga = None if grad_alpha is None else _f32c(grad_alpha, device)
+                    _lib.check(lib.gsr_backward_camera(C.byref(s), C.byref(c), state.cap, _ptr(geom), geom.numel(),
+                                                       _ptr(binning), binning.numel(), _ptr(img), img.numel(),
+                                                       _ptr(radii), _ptr(grad_out_color), _ptr(ga), _ptr(scratch), sbytes,
+                                                       C.byref(gr), C.byref(cam), st), "gsr_backward_camera")
+                    cam_grads = (d_view.view(rs.viewmatrix.shape), d_proj.view(rs.projmatrix.shape),
+                                 d_cam.view(rs.campos.shape))
+                elif grad_alpha is not None:
                     grad_alpha = _f32c(grad_alpha, device)
                     _lib.check(lib.gsr_backward_alpha(C.byref(s), C.byref(c), state.cap, _ptr(geom), geom.numel(),
                                                       _ptr(binning), binning.numel(), _ptr(img), img.numel(),
@@ -276,8 +294,14 @@ class _RasterizeGaussians(torch.autograd.Function):
                 if scales.numel() == 0:  # cov3D_precomp path: the reference leaves these at their zero-fill
                     dL_dscales.zero_(); dL_drotations.zero_()
         # same slots as the reference (__init__.py:213-223); autograd drops grads of inputs that do not need one
-        return (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,
-                None, None)
+        grads = (dL_dmeans3D, dL_dmeans2D, dL_dsh, dL_dcolors, dL_dopacity, dL_dscales, dL_drotations, dL_dcov3D,
+                 None, None)
+        if ctx.camera_grad:
+            if P == 0:
+                z = lambda t: torch.zeros_like(t, dtype=torch.float32)
+                cam_grads = (z(rs.viewmatrix), z(rs.projmatrix), z(rs.campos))
+            grads = grads + cam_grads
+        return grads
 
 
 class _RasterizeGaussiansRaw(torch.autograd.Function):
@@ -327,13 +351,17 @@ class _RasterizeGaussiansRaw(torch.autograd.Function):
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings, return_alpha: bool = False):
+    def __init__(self, raster_settings, return_alpha: bool = False, camera_grad: bool = False):
         """``return_alpha=True`` (opt-in, not in the reference) appends a fourth output to ``forward``: the alpha image
         ``1 - final_T`` [1,H,W] (the reference keeps final_T as ``accum_alpha`` but never returns it); it is
-        differentiable like the colour."""
+        differentiable like the colour.
+        ``camera_grad=True`` (opt-in, not in the reference): ``raster_settings.viewmatrix / projmatrix / campos`` become
+        differentiable inputs -- their ``.grad`` is filled by the backward (gsr_backward_camera), each array treated as an
+        independent input exactly as the forward reads it."""
         super().__init__()
         self.raster_settings = raster_settings
         self.return_alpha = bool(return_alpha)
+        self.camera_grad = bool(camera_grad)
 
     def forward_raw(self, means3D, means2D, opacity_logits, features_dc, features_rest, log_scales, raw_rotations):
         """Opt-in fused-activation call (not part of the reference API): the arguments are the scene model's raw
@@ -384,7 +412,7 @@ class GaussianRasterizer(nn.Module):
             cov3D_precomp = empty
 
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, raster_settings, self.return_alpha)
+                                   cov3D_precomp, raster_settings, self.return_alpha, self.camera_grad)
 
     def apply_weights(self, means3D, means2D, opacities, shs=None, weights=None, scales=None, rotations=None,
                       cov3Ds_precomp=None, cnt=None, image_weights=None):

@@ -7,7 +7,8 @@ items to the ~R/V * P_total / world candidates a rank really blends.
 
   forward   gsr_sparse_preprocess  (preprocess + ordered peer stores of the records into every destination's candidate
                                     array, over NVLink peer mappings)
-            all-reduce of the [world, 8] count matrix  (the barrier after the push; every rank learns every segment size)
+            gsr_peer_barrier(with_matrix_row)  (flags + count rows through peer memory: the barrier after the push;
+                                    every rank learns every segment size -- no NCCL call in the step)
             gsr_sparse_order / gsr_shard_render on the candidates of the owned tile rows
             gsr_frame_broadcast (peer stores of the owned rows into every rank's frame) + barrier
   backward  gsr_shard_backward_render -> gsr_sparse_return (peer stores of the accumulator rows to their owners) + barrier
@@ -34,6 +35,7 @@ from .rasterizer import GaussianRasterizationSettings, _f32c, _make_cloud, _make
 from .sharded import ACC_STRIDE, Exchange, PeerWorkspace, ShardPlan, shard_slice
 
 MAXP = 8  # GSR_MAX_PEERS
+CTRL_BYTES, CTRL_MATRIX_OFFSET = 512, 64   # GSR_PEER_CTRL_BYTES, GSR_PEER_CTRL_MATRIX_OFFSET
 
 
 def _align(n: int, a: int = 256) -> int:
@@ -42,15 +44,17 @@ def _align(n: int, a: int = 256) -> int:
 
 class SparseRank:
     """Buffers of one rank for ONE in-flight forward/backward: local (owner-side) workspace, the peer-visible block
-    ``[frame 4*H*W floats | candidate workspace]`` and small bookkeeping tensors. ``seg_cap`` may change from step to
-    step (it only selects how much of the allocated candidate workspace is used); ``cap_alloc`` is fixed."""
+    ``[control words 512 B | frame 4*H*W floats | candidate workspace]`` and small bookkeeping tensors. ``seg_cap`` may
+    change from step to step (it only selects how much of the allocated candidate workspace is used); ``cap_alloc`` is
+    fixed. ``matrix`` (the [world, 8] segment counts) is a view into the control words: peers write their rows there."""
 
     def __init__(self, plan: ShardPlan, device, W: int, H: int, cap_alloc: Optional[int] = None,
                  exchange: Optional[Exchange] = None):
         lib = _lib.load()
         self.plan, self.device, self.W, self.H = plan, device, int(W), int(H)
         self.cap_alloc = int(cap_alloc if cap_alloc is not None else max(plan.slice_len, 1))
-        self.frame_bytes = _align(16 * self.W * self.H)
+        self.frame_off = CTRL_BYTES
+        self.frame_bytes = CTRL_BYTES + _align(16 * self.W * self.H)   # offset of the candidate workspace in the block
         self.cand_bytes_alloc = lib.gsr_sparse_candidate_bytes(plan.world, self.cap_alloc)
         if self.cand_bytes_alloc == 0:
             _lib.check(-2, "gsr_sparse_candidate_bytes")
@@ -58,7 +62,6 @@ class SparseRank:
         self.local_bytes = lib.gsr_sparse_local_bytes(max(plan.slice_len, 1))
         with torch.cuda.device(device):
             self.local = torch.empty(self.local_bytes, dtype=torch.uint8, device=device)
-            self.matrix = torch.zeros(plan.world, MAXP, dtype=torch.int32, device=device)
             self.radii_local = torch.zeros(max(plan.slice_len, 1), dtype=torch.int32, device=device)
             self.pinned = torch.zeros(2, dtype=torch.int32).pin_memory()
             self.peer = None
@@ -70,6 +73,13 @@ class SparseRank:
                 self.block = torch.empty(self.total_bytes, dtype=torch.uint8, device=device)
                 self.base_ptrs = [None] * plan.world
                 self.base_ptrs[plan.rank] = self.block.data_ptr()
+            self.block[:CTRL_BYTES].zero_()
+            self.matrix = self.block[CTRL_MATRIX_OFFSET:CTRL_MATRIX_OFFSET + 4 * MAXP * MAXP].view(torch.int32).view(MAXP, MAXP)[:plan.world]
+        self.epoch = 0
+        if exchange is not None:
+            torch.cuda.synchronize(device)
+            exchange.barrier(device)      # every rank's control words are zero before anybody raises a flag
+            torch.cuda.synchronize(device)
         self.scratch: dict = {}
         self.index = 0
         self._arrays()
@@ -77,7 +87,8 @@ class SparseRank:
     def _arrays(self):
         w = self.plan.world
         self.cand_ptr_array = (C.c_void_p * w)(*[(p + self.frame_bytes) if p is not None else None for p in self.base_ptrs])
-        self.frame_ptr_array = (C.c_void_p * w)(*self.base_ptrs)
+        self.frame_ptr_array = (C.c_void_p * w)(*[(p + self.frame_off) if p is not None else None for p in self.base_ptrs])
+        self.ctrl_ptr_array = (C.c_void_p * w)(*self.base_ptrs)
 
     @property
     def cand(self) -> torch.Tensor:
@@ -85,7 +96,7 @@ class SparseRank:
 
     @property
     def frame(self) -> torch.Tensor:
-        return self.block[:16 * self.W * self.H].view(torch.float32).view(4, self.H, self.W)
+        return self.block[self.frame_off:self.frame_off + 16 * self.W * self.H].view(torch.float32).view(4, self.H, self.W)
 
     def get(self, name: str, numel: int, dtype, grow: float = 1.0) -> torch.Tensor:
         t = self.scratch.get(name)
@@ -95,6 +106,7 @@ class SparseRank:
 
     def close(self):
         self.scratch.clear()
+        self.matrix = None
         if self.peer is not None:
             self.block = None
             self.peer.close()
@@ -145,7 +157,8 @@ def sparse_preprocess(rk: SparseRank, rs: GaussianRasterizationSettings, means3D
         st.cplan = _cplan(plan, cap)
         c = _make_cloud(plan.count, *[st.inputs[i] for i in (0, 3, 1, 2, 4, 5, 6)])
         stream = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
-        rk.matrix.zero_()
+        # (the count matrix is never zeroed: every step each rank rewrites its whole row, here and -- through
+        # peer_barrier(with_row=True) -- in every peer's copy; a zero-fill could wipe a faster peer's fresh row)
         cand_bytes = lib.gsr_sparse_candidate_bytes(plan.world, cap)
         _lib.check(lib.gsr_sparse_preprocess(C.byref(st.s), C.byref(c), C.byref(st.cplan), _ptr(rk.local), rk.local_bytes,
                                              _ptr(rk.radii_local), rk.cand_ptr_array, cand_bytes,
@@ -199,6 +212,18 @@ def frame_broadcast(rk: SparseRank):
         stream = C.c_void_p(torch.cuda.current_stream(rk.device).cuda_stream)
         _lib.check(lib.gsr_frame_broadcast(C.byref(own), rk.W, rk.H, _ptr(rk.frame), rk.frame_ptr_array, stream),
                    "gsr_frame_broadcast")
+
+
+def peer_barrier(rk: SparseRank, with_row: bool = False):
+    """Cross-rank barrier on the compute stream through the control words of the peer-mapped blocks (gsr_peer_barrier):
+    work queued behind it starts once every rank has reached the same point; with `with_row` this rank's row of the
+    count matrix is first copied into every peer's matrix (the all-gather of the segment sizes)."""
+    lib = _lib.load()
+    rk.epoch += 1
+    with torch.cuda.device(rk.device):
+        stream = C.c_void_p(torch.cuda.current_stream(rk.device).cuda_stream)
+        _lib.check(lib.gsr_peer_barrier(rk.plan.world, rk.plan.rank, rk.ctrl_ptr_array, rk.epoch & 0xFFFFFFFF,
+                                        1 if with_row else 0, stream), "gsr_peer_barrier")
 
 
 def sparse_backward_render(st: SparseStep, grad_out_color: torch.Tensor) -> torch.Tensor:
@@ -257,8 +282,9 @@ def sparse_backward_preprocess(st: SparseStep):
 
 def next_capacity(max_count: int, cap_alloc: int) -> int:
     """Segment capacity for the next step from the largest segment seen (identical on every rank: the count matrix is
-    all-reduced): 25 % headroom, 4096-slot granularity, never above what was allocated."""
-    want = int(max_count * 1.25) + 4096
+    all-reduced): 10 % headroom (every slot of headroom is a hole the depth sort still carries), 4096-slot granularity,
+    never above what was allocated. A frame that overflows is simply redone with the exact requirement."""
+    want = int(max_count * 1.10) + 4096
     return max(1, min(cap_alloc, (want + 4095) // 4096 * 4096))
 
 
@@ -316,7 +342,7 @@ class _SparseShardedRasterize(torch.autograd.Function):
         while True:
             st = sparse_preprocess(rk, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, pool.cap)
             _mark("preprocess+push")
-            exchange.all_reduce_sum(rk.matrix)             # counts + barrier: every push has landed
+            peer_barrier(rk, with_row=True)                # counts + barrier: every push has landed
             _mark("count all-reduce")
             R, max_count = sparse_order(st)
             _mark("order")
@@ -332,7 +358,7 @@ class _SparseShardedRasterize(torch.autograd.Function):
         sparse_render(st, frame[:3], frame[3:])
         _mark("bin+blend")
         frame_broadcast(rk)
-        exchange.barrier(device)
+        peer_barrier(rk)
         out = frame.clone()                                 # the peer-visible frame is overwritten by the next step
         _mark("frame broadcast+barrier")
         ctx.st, ctx.exchange = st, exchange
@@ -350,7 +376,7 @@ class _SparseShardedRasterize(torch.autograd.Function):
         acc = sparse_backward_render(st, grad_out_color)
         _mark("blend backward")
         sparse_return(st, acc)
-        exchange.barrier(grad_out_color.device)
+        peer_barrier(st.rk)
         _mark("return push+barrier")
         grads = sparse_backward_preprocess(st)
         _mark("gather+preprocess backward")

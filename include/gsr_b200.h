@@ -150,6 +150,30 @@ GSR_API int gsr_backward_alpha(const gsr_settings* s, const gsr_cloud* c, int32_
                        const float* dL_dout_alpha, void* scratch, size_t scratch_bytes, const gsr_grads* grads,
                        void* stream);
 
+/* ---- camera gradients (north star: backward over {..., viewmatrix}; opt-in, the reference has none) -------------
+ * The reference's autograd returns None for the raster settings (diff_gaussian_rasterization/__init__.py:213-223), so
+ * there is nothing to be drop-in for; this entry point extends gsr_backward_alpha with
+ *   dL/dviewmatrix [16], dL/dprojmatrix [16], dL/dcampos [3]
+ * for the three camera arrays of gsr_settings treated as INDEPENDENT inputs, exactly as the forward reads them (the
+ * view matrix through t = view*mean and the rotation W of the EWA Jacobian product, cuda_rasterizer/forward.cu:74-113;
+ * the full projection through p_hom, :196-200; the camera centre through the SH view direction, :20-71). The same
+ * conventions as the mean gradient apply (clamped t.x / t.y pass no gradient, backward.cu:205-212). A caller that
+ * derives projmatrix and campos from the view matrix (scene/cameras.py:92-95) chains the three in its own autograd.
+ * Checked against central finite differences of the fp64 CPU oracle (tests/test_parity_gpu.py). */
+typedef struct gsr_camera_grads {
+  float* dL_dviewmatrix; /* [16] same layout as gsr_settings.viewmatrix; entries the forward never reads stay 0 */
+  float* dL_dprojmatrix; /* [16] */
+  float* dL_dcampos;     /* [3]  */
+  void* scratch;         /* gsr_camera_scratch_bytes(P) bytes of device memory */
+  size_t scratch_bytes;
+} gsr_camera_grads;
+GSR_API size_t gsr_camera_scratch_bytes(int32_t P);
+GSR_API int gsr_backward_camera(const gsr_settings* s, const gsr_cloud* c, int32_t num_rendered, const void* geometry,
+                        size_t geometry_bytes, const void* binning, size_t binning_bytes, const void* image,
+                        size_t image_bytes, const int32_t* radii, const float* dL_dout_color,
+                        const float* dL_dout_alpha /* may be NULL */, void* scratch, size_t scratch_bytes,
+                        const gsr_grads* grads, const gsr_camera_grads* camera, void* stream);
+
 /* ---- markVisible: present[i] = view-space z > 0.2 (auxiliary.h:139-164) ------------------------------- */
 GSR_API int gsr_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
                      uint8_t* present, void* stream);
@@ -333,6 +357,19 @@ GSR_API int gsr_sparse_backward_preprocess(const gsr_settings* s, const gsr_clou
                                    const void* local_ws, size_t local_bytes, const int32_t* radii_local,
                                    const void* cand_ws, size_t cand_bytes, void* acc_slice /* [shard.P,12] scratch */,
                                    size_t acc_bytes, const gsr_grads* grads, void* stream);
+/* Cross-rank barrier over peer memory (replaces the 4-byte NCCL all-reduces of the dense scheme: ~5 us instead of
+ * ~25 us at 8 GPUs). Every rank's peer-visible block starts with GSR_PEER_CTRL_BYTES of control words, zeroed once at
+ * creation: flags[rank] = number of the last barrier that rank reached, and the [GSR_MAX_PEERS, GSR_MAX_PEERS] int32
+ * count matrix at byte GSR_PEER_CTRL_MATRIX_OFFSET (row s = n[s -> d], written by rank s: gsr_sparse_preprocess takes
+ * counts_row = own row of the OWN block). peer_ctrl[r] is rank r's block as mapped here. `epoch` must increase by one per
+ * barrier on this block, identically on every rank. with_matrix_row != 0 first copies this rank's row into every
+ * peer's matrix, so that after the barrier every rank holds the complete matrix. Work queued on `stream` behind this
+ * call starts only after every rank has reached the same barrier (a rank that never arrives costs ~2 s and sets the
+ * block's error word instead of hanging the GPU). */
+#define GSR_PEER_CTRL_BYTES 512
+#define GSR_PEER_CTRL_MATRIX_OFFSET 64
+GSR_API int gsr_peer_barrier(int32_t world, int32_t rank, void* const* peer_ctrl /* [world] host */, uint32_t epoch,
+                     int32_t with_matrix_row, void* stream);
 /* Copies the tile rows this rank owns of its [4,H,W] frame (colour + depth) into the frames of all other ranks
  * (128-bit peer stores): with one writer per pixel this replaces the all-reduce of the frames. A cross-rank barrier
  * must follow before the frames are read. */

@@ -267,6 +267,53 @@ def test_alpha_output_matches_reference_accum_alpha_and_is_differentiable():
         assert rel_l2(g_a[k], g_b[k]) <= 2e-5, (k, rel_l2(g_a[k], g_b[k]))
 
 
+def test_camera_gradients_match_finite_differences_of_the_fp64_oracle():
+    """North star: backward over {..., viewmatrix}. The reference has no camera gradient, so the check is first
+    principles: d/d(camera entry) of loss = sum(color * G), with viewmatrix / projmatrix / campos as independent
+    inputs, against CENTRAL FINITE DIFFERENCES of the fp64 CPU oracle's forward (float32-representable steps)."""
+    from gaussianeditor_b200.rasterizer import GaussianRasterizer
+    dev = "cuda"
+    cloud, _ = synth.make_config("c3", P=4000)
+    cam = synth.ring_cameras(8, 4.5, 15.0, 96, 64, 61.0)[3]
+    H, W = cam.image_height, cam.image_width
+    bg = (0.2, 0.1, 0.3)
+    G = np.random.default_rng(31).uniform(0.5, 1.5, size=(3, H, W)).astype(np.float32)
+    ct = cloud_tensors(cloud, dev)
+    rs = settings_from(cam, bg, cloud.sh_degree, dev)
+    view = rs.viewmatrix.clone().requires_grad_(True)
+    proj = rs.projmatrix.clone().requires_grad_(True)
+    cpos = rs.campos.clone().requires_grad_(True)
+    rs = rs._replace(viewmatrix=view, projmatrix=proj, campos=cpos)
+    out = GaussianRasterizer(rs, camera_grad=True)(means3D=ct["means3D"], means2D=torch.zeros_like(ct["means3D"]),
+                                                   opacities=ct["opacities"], shs=ct["shs"], scales=ct["scales"],
+                                                   rotations=ct["rotations"])
+    (out[0] * torch.from_numpy(G).to(dev)).sum().backward()
+    got = dict(viewmatrix=view.grad.cpu().numpy().astype(np.float64), projmatrix=proj.grad.cpu().numpy().astype(np.float64),
+               campos=cpos.grad.cpu().numpy().astype(np.float64))
+
+    def loss(**over):
+        f = cpu_oracle.forward_from(cloud, cam, bg, f32=False, **over)
+        v = float((f.color * G).sum())
+        f.close()
+        return v
+
+    base = dict(viewmatrix=cam.viewmatrix.astype(np.float32), projmatrix=cam.projmatrix.astype(np.float32),
+                campos=cam.campos.astype(np.float32))
+    h = np.float32(2.0 ** -11)
+    for name, arr in base.items():
+        fd = np.zeros(arr.shape, np.float64)
+        for idx in np.ndindex(arr.shape):
+            if name != "campos" and (idx[1] == 3 if name == "viewmatrix" else idx[1] == 2):
+                continue   # entries the forward never reads (column 3 of the transposed view, depth row of the projection)
+            ap, am = arr.copy(), arr.copy()
+            ap[idx] += h; am[idx] -= h
+            fd[idx] = (loss(**{name: ap}) - loss(**{name: am})) / float(ap[idx] - am[idx])
+        err = np.linalg.norm(got[name] - fd) / max(np.linalg.norm(fd), 1e-30)
+        assert np.linalg.norm(fd) > 0 and err <= 2e-2, (name, err, got[name], fd)
+    # entries the forward never reads get exactly zero
+    assert np.all(got["viewmatrix"][:, 3] == 0) and np.all(got["projmatrix"][:, 2] == 0)
+
+
 def test_full_size_properties_config3():
     """BASELINE config 3 (1M Gaussians, 1600x1200): size-independent properties at full size."""
     cloud, cams = synth.make_config("c3")

@@ -188,6 +188,8 @@ def test_sparse_exchange_virtual_ranks_match_single_gpu(world, cap_mode):
     def forward(cap):
         steps = []
         for rk in ranks:
+            rk.matrix.zero_()    # the "all-reduce" below is a sum: rows of the other ranks must start at zero
+        for rk in ranks:
             sl = lambda t: S.shard_slice(t, rk.plan)
             steps.append(SS.sparse_preprocess(rk, rs, sl(full["means3D"]), sl(full["shs"]), empty, sl(full["opacities"]),
                                               sl(full["scales"]), sl(full["rotations"]), empty, cap))
