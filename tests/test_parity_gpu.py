@@ -270,7 +270,12 @@ def test_alpha_output_matches_reference_accum_alpha_and_is_differentiable():
 def test_camera_gradients_match_finite_differences_of_the_fp64_oracle():
     """North star: backward over {..., viewmatrix}. The reference has no camera gradient, so the check is first
     principles: d/d(camera entry) of loss = sum(color * G), with viewmatrix / projmatrix / campos as independent
-    inputs, against CENTRAL FINITE DIFFERENCES of the fp64 CPU oracle's forward (float32-representable steps)."""
+    inputs, against CENTRAL FINITE DIFFERENCES of the fp64 CPU oracle's forward (float32-representable steps).
+    Tolerance 6 %: the pipeline is discontinuous where a pixel crosses a splat's alpha = 1/255 contour or the T < 1e-4
+    cut, and the analytic gradient (the reference's, for every parameter) ignores the motion of those contours while a
+    finite difference integrates it -- the fp64 differences themselves move by 2-7 % between step sizes 2^-9 .. 2^-13
+    on this scene. The formulas are pinned exactly (1e-9) against autograd of the smooth per-Gaussian forward map in
+    tests/test_camera_grad_math.py (CPU)."""
     from gaussianeditor_b200.rasterizer import GaussianRasterizer
     dev = "cuda"
     cloud, _ = synth.make_config("c3", P=4000)
@@ -309,7 +314,7 @@ def test_camera_gradients_match_finite_differences_of_the_fp64_oracle():
             ap[idx] += h; am[idx] -= h
             fd[idx] = (loss(**{name: ap}) - loss(**{name: am})) / float(ap[idx] - am[idx])
         err = np.linalg.norm(got[name] - fd) / max(np.linalg.norm(fd), 1e-30)
-        assert np.linalg.norm(fd) > 0 and err <= 2e-2, (name, err, got[name], fd)
+        assert np.linalg.norm(fd) > 0 and err <= 6e-2, (name, err, got[name], fd)
     # entries the forward never reads get exactly zero
     assert np.all(got["viewmatrix"][:, 3] == 0) and np.all(got["projmatrix"][:, 2] == 0)
 
