@@ -344,9 +344,13 @@ def alg_bytes(desc, M, Msh, W, H):
         # in: mean12+scale12+rot16+opacity4 for all P, SH rows only for z-visible; out: record48 (visible) + radii4+tiles4+clamped1+key4+ident4
         "preprocess_fwd": P * 44 + V * 12 * Msh + V * 48 + P * 17,
         "depth_order_scan": 4 * (8 + 8) * P + 4 * P + 8 * P + 4 * P,   # 4 radix passes r+w of (key,val) + hist + scan gather/write
+        # binning_variant 0 (CUB): emit kernel + histogram + 2 passes over (u16 key, u32 val) + ranges from the sorted keys
         "emit_instances": P * 8 + V * (16 + 4 + 4) + 8 * R,
-        "tile_sort": (2 * (8 + 8) + 4) * R,                              # 2 passes r+w of (key,val) + histogram read
-        "tile_ranges": 4 * R + 8 * Nt,
+        # binning_variant 1 (tile_binning.cu): pass 1 generates (reads offsets/order/record/radius of the visible
+        # Gaussians) and writes 6 B per instance, pass 2 reads 6 B and writes 6 B
+        "tile_sort": 18 * R + 28 * V + 4 * P,
+        # tile_count + tile_prefix: replicas of the difference array in, ranges out (no pass over the instances)
+        "tile_ranges": 8 * Nt + 4 * 17 * (Nt + 200),
         "render_fwd": (4 + 48) * R + 8 * Nt + 24 * npix,                 # upper bound: whole lists; early-out reads less
         "render_bwd": (4 + 48) * R + 20 * npix + 36 * R + 48 * P,
         "preprocess_bwd": P * 5 + V * (48 + 44 + 12 * Msh) + P * (56 + 24 + 12 * M),
@@ -691,7 +695,8 @@ def main():
         ach = ab[dom] / (stages[dom] * 1e-3) / 1e9
         traffic, issue = None, None
         try:  # DRAM bytes and instruction count per launch from the committed ncu --set full capture of the same command
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tp = os.path.join(ROOT, "profiles", "r02_traffic.json")
+            with open(tp if os.path.exists(tp) else os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
                 kd = json.load(f)["kernels"][dom]
             traffic = kd["dram_bytes"]
             # second lens for the issue-bound render kernels: warp instructions per launch (ncu) / live kernel time,
