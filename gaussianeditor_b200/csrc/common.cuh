@@ -43,14 +43,14 @@ struct GeometryWS {
   size_t total;
 };
 // (gx+1)*(gy+1) <= 2*65536 + 1 for every grid with gx*gy < 65536 tiles (the limit of the 16-bit tile keys)
-constexpr int MAX_TILE_DIFF = 2 * 65536 + 64;
+constexpr int MAX_TILE_DIFF = 4 * (2 * 65536 + 64);  // 2 MB: room for 64 replicas of a 1600x1200 grid
 // The corner updates are global atomics and a scene concentrates them on the few hundred entries around the screen
 // centre (same-address atomics serialise in L2: measured +65 us on the 1M-Gaussian preprocess). The reservation is used
-// for up to 16 REPLICAS of the array (Gaussian i updates replica i & (copies-1)); the readers add the replicas up.
+// for up to 64 REPLICAS of the array (Gaussian i updates replica i & (copies-1)); the readers add the replicas up.
 inline int tile_diff_copies(int gx, int gy) {
   const long long nent = (long long)(gx + 1) * (gy + 1);
   int c = 1;  // + 1: behind the replicas lies their sum, written by tile_count_kernel and read by tile_prefix_kernel
-  while (c < 16 && (2LL * c + 1) * nent <= MAX_TILE_DIFF) c *= 2;
+  while (c < 64 && (2LL * c + 1) * nent <= MAX_TILE_DIFF) c *= 2;
   return c;
 }
 struct BinningWS {

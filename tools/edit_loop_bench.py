@@ -13,12 +13,18 @@ def slim(d):
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 P = int(sys.argv[2]) if len(sys.argv) > 2 else None
+# every arm first runs a short untimed loop: the first loop of a process pays for the caching allocator's growth
+# (workspaces of new sizes after every densification), pinned buffers and lazy CUDA module loading -- 8.8 vs 3.5 ms/step
+# measured for the same code as first vs second loop
+for cls in (GaussianRasterizer,):
+    edit_loop.run_edit_loop(cls, steps=40, P=P, densification_interval=20)
 out = {"config": "c5: 500k Gaussians, SH deg 3, 512x512, 48 ring cameras, guidance stubbed by a fixed noisy target, L1 loss",
        "ours": slim(edit_loop.run_edit_loop(GaussianRasterizer, steps=steps, P=P)),
        "ours_fused_activations": slim(edit_loop.run_edit_loop(GaussianRasterizer, steps=steps, P=P, fused_activations=True))}
 try:
     from oracle import ref_cuda, ref_torch
     if ref_cuda.available():
+        edit_loop.run_edit_loop(ref_torch.RefGaussianRasterizer, steps=40, P=P, densification_interval=20)
         out["reference"] = slim(edit_loop.run_edit_loop(ref_torch.RefGaussianRasterizer, steps=steps, P=P))
         out["step_speedup"] = out["reference"]["ms_per_step"] / out["ours"]["ms_per_step"]
         out["render_speedup"] = out["reference"]["render_ms"] / out["ours"]["render_ms"]
