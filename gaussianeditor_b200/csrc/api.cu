@@ -624,6 +624,7 @@ int gsr_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "profile")) g_opt.profile = (int)value;
   else if (!strcmp(name, "tile_key_bits")) g_opt.tile_key_bits = (int)value;
   else if (!strcmp(name, "binning_variant")) g_opt.binning_variant = (int)value;
+  else if (!strcmp(name, "depth_sort_variant")) g_opt.depth_sort_variant = (int)value;
   else if (!strcmp(name, "stats")) {
     if (value && !g_stats_dev) {
       if (cudaMalloc((void**)&g_stats_dev, 16 * sizeof(unsigned long long)) != cudaSuccess) return check_cuda(cudaGetLastError(), "stats alloc");
@@ -653,6 +654,7 @@ int64_t gsr_get_option(const char* name) {
   if (!strcmp(name, "profile")) return g_opt.profile;
   if (!strcmp(name, "tile_key_bits")) return g_opt.tile_key_bits;
   if (!strcmp(name, "binning_variant")) return g_opt.binning_variant;
+  if (!strcmp(name, "depth_sort_variant")) return g_opt.depth_sort_variant;
   return -1;
 }
 int64_t gsr_launch_count(void) { return g_launches; }

@@ -324,6 +324,8 @@ bool carve_geometry(void* base, int P, GeometryWS& ws) {
     return false;
   }
   ws.cub_temp_bytes = t1 > t2 ? t1 : t2;
+  const size_t t3 = depth_sort_scratch_bytes((int)n);  // depth_sort.cu (default depth order): status words + ping-pong arrays
+  if (t3 > ws.cub_temp_bytes) ws.cub_temp_bytes = t3;
   ws.cub_temp = take(ws.cub_temp_bytes);
   ws.total = off;
   return true;
@@ -379,6 +381,15 @@ int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* n
                              bool debug) {
   // num_rendered_host == nullptr: the caller already fetched the count from g.R_dev (tile_binning path)
   const int P = c.P;
+  if (g_opt.depth_sort_variant == 1) {
+    int rc = run_depth_sort_own(P, g, st, debug);
+    if (rc) return rc;
+    if (num_rendered_host) {
+      cudaError_t e2 = cudaMemcpyAsync(num_rendered_host, g.offsets + (P - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+      if (e2 != cudaSuccess) return check_cuda(e2, "num_rendered readback");
+    }
+    return GSR_OK;
+  }
   size_t tb = g.cub_temp_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(g.cub_temp, tb, (const uint32_t*)g.depth_keys, g.depth_keys_sorted,
                                                   (const uint32_t*)g.ident, g.depth_order, P, 0, 32, st);

@@ -50,7 +50,9 @@ constexpr int MAX_TILE_DIFF = 4 * (2 * 65536 + 64);  // 2 MB: room for 64 replic
 inline int tile_diff_copies(int gx, int gy) {
   const long long nent = (long long)(gx + 1) * (gy + 1);
   int c = 1;  // + 1: behind the replicas lies their sum, written by tile_count_kernel and read by tile_prefix_kernel
-  while (c < 64 && (2LL * c + 1) * nent <= MAX_TILE_DIFF) c *= 2;
+  // up to 64 replicas, but no more than ~0.5 MB in total: beyond that the memset and the replica sum cost more than the
+  // contention they remove (measured at 1600x1200: 16 replicas 0.075 ms, 64 replicas 0.081 ms for the preprocess stage)
+  while (c < 64 && (2LL * c + 1) * nent <= MAX_TILE_DIFF / 4) c *= 2;
   return c;
 }
 struct BinningWS {
@@ -93,11 +95,12 @@ constexpr int ACC_STRIDE = 12;
 // ---- options -----------------------------------------------------------------------------------------
 struct Options {
   int render_fwd_variant = 3;  // 0 CTA/tile, 1/2/3 = 1/2/4 warps per tile
-  int render_bwd_variant = 4;  // 0 CTA/tile, 1/2/3 branchy 1/2/4 warps per tile, 4/5/6/7 branch-light variants
+  int render_bwd_variant = 14;  // 0 CTA/tile, 1/2/3 branchy, 4..9 branch-light, 10/11 mask-skip, 12..14 register caps (14: 96 regs + hit-skip)
   int preprocess_variant = 1;
   int profile = 0;
   int tile_key_bits = 16;
   int binning_variant = 1;     // 0 = emit kernel + CUB tile sort + tile_ranges, 1 = tile_binning.cu
+  int depth_sort_variant = 0;  // 0 = CUB radix sort + CUB scan (default: faster at 1M keys), 1 = depth_sort.cu
 };
 enum Stage { ST_PRE_FWD = 0, ST_DEPTH_SCAN, ST_EMIT, ST_TILE_SORT, ST_RANGES, ST_RENDER_FWD, ST_RENDER_BWD, ST_PRE_BWD, ST_APPLY_W };
 // RAII stage timer: records two events on `st` when profiling is on, otherwise free.
@@ -123,6 +126,9 @@ int validate_cloud(const gsr_settings* s, const gsr_cloud* c);  // argument chec
 int launch_preprocess_fwd(const gsr_settings& s, const gsr_cloud& c, const GeometryWS& g, int32_t* radii,
                           cudaStream_t st, SplatRecord* const* peer_records = nullptr, int npeers = 0, bool raw = false,
                           const float* features_rest = nullptr, bool count_tiles = false);
+// depth_sort.cu: depth order + offsets scan without CUB; scratch lives in GeometryWS::cub_temp
+size_t depth_sort_scratch_bytes(int P);
+int run_depth_sort_own(int P, const GeometryWS& g, cudaStream_t st, bool debug);
 int run_depth_order_and_scan(const gsr_cloud& c, const GeometryWS& g, int32_t* num_rendered_host, cudaStream_t st,
                              bool debug);
 // Sharded path: recompute tiles_touched (owned tile rows only) and the sort identity for all P gathered Gaussians.

@@ -307,7 +307,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int NSB, int MINB, bool SKIP = false>
+template <int NSB, int MINB, bool SKIP = false, bool MASKSKIP = false>
 __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(const BwdArgs a, const int ntiles) {
   __shared__ float4 s_stage[BW_WARPS][3][32];
   __shared__ uint32_t s_id[BW_WARPS][32];
@@ -410,6 +410,10 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
       bool near = false;
 #pragma unroll
       for (int k = 0; k < NSB; k++) {
+        if (MASKSKIP && !((m >> k) & 1u)) {  // warp-uniform: the splat's alpha >= 1/255 ellipse misses this sub-block
+          pw[k] = 1.0f; G[k] = 0.f; al[k] = 0.f;
+          continue;
+        }
         const int c = k & 1, r = k >> 1;
         const float s = __fmaf_rn(dxv[c], dxA[c], t0[r]);
         pw[k] = __fmaf_rn(s, -0.5f, -__fmul_rn(dxB[c], dyv[r]));
@@ -420,6 +424,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
       if (near) {  // rare: too close to the 1/255 threshold to call with ex2.approx -> the forward's exact arithmetic
 #pragma unroll
         for (int k = 0; k < NSB; k++) {
+          if (MASKSKIP && !((m >> k) & 1u)) continue;
           G[k] = expf(pw[k]);
           al[k] = fminf(0.99f, __fmul_rn(s1.y, G[k]));
         }
@@ -442,6 +447,7 @@ __global__ void __launch_bounds__(BW_WARPS * 32, MINB) render_bwd_flat_kernel(co
       for (int k = 0; k < NSB; k++) {
         // (alpha, G) = (0, 0) makes every update below an exact no-op: 1/(1-0) = 1, +0 contributions
         if (SKIP && !((hitk >> k) & 1u)) continue;
+        if (MASKSKIP && !((m >> k) & 1u)) continue;
         hit_update(ps[k], g, dxv[k & 1], dyv[k >> 1], G[k], al[k], s1.y, s2.x, s2.y, s2.z);
       }
       float m8;
@@ -556,6 +562,16 @@ int launch_render_bwd(const gsr_settings& s, const GeometryWS& g, const BinningW
     render_bwd_flat_kernel<4, 1, true><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   } else if (v == 9) {
     render_bwd_flat_kernel<8, 1, true><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 12) {  // register caps: 5 / 6 CTAs per SM, with and without the hit-skip
+    render_bwd_flat_kernel<4, 5><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 13) {
+    render_bwd_flat_kernel<4, 6, true><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 14) {
+    render_bwd_flat_kernel<4, 5, true><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 10) {  // variant 4 + sub-blocks outside the splat's mask skipped with warp-uniform branches
+    render_bwd_flat_kernel<4, 1, false, true><<<(ntiles * 2 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
+  } else if (v == 11) {  // the same for the quarter-tile mapping
+    render_bwd_flat_kernel<2, 1, false, true><<<(ntiles * 4 + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   } else {
     render_bwd_warp_kernel<8><<<(ntiles + BW_WARPS - 1) / BW_WARPS, BW_WARPS * 32, 0, st>>>(a, ntiles);
   }

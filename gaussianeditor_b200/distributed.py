@@ -4,9 +4,9 @@ The path shards over VIEWS: every rank holds the whole cloud and renders its own
 independent, so the data path needs no collective -- "weak" scaling, bench.py --gpus N).  When the replicas are
 used for data-parallel optimisation the per-Gaussian gradients are summed across ranks with one all-reduce per
 parameter group; that is the only exchange step and it lives outside the rasterizer, exactly where a
-GaussianEditor batch>1 loop would put it.  (The Gaussian-index-sharded variant of SURVEY.md 8(e) -- splat
-all-gather, tile-owned render, 2-D gradient reduce-scatter -- is only needed when a cloud exceeds one GPU's
-180 GB, which none of the BASELINE configs does; see DESIGN.md "Multi-GPU".)
+GaussianEditor batch>1 loop would put it.  The Gaussian-index-sharded path of SURVEY.md 8(e) (BASELINE config 4: one
+view, the cloud split over the ranks, tile rows owned round-robin) is a separate module -- sharded.py for the dense
+exchange, sparse_sharded.py + csrc/sparse_exchange.cu for the default sparse peer-memory exchange; DESIGN.md 7.2.
 
 Works with the `nccl` backend on GPUs and with `gloo` on CPU tensors (used by the world_size-2 CPU tests).
 """

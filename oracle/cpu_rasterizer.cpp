@@ -10,7 +10,8 @@
 // PARITY PINNING: the reference ships no tests, golden vectors or CPU path for this
 // code, so this restatement is pinned two ways instead:
 //   (1) against the reference's own CUDA sources compiled unmodified into
-//       oracle/_ref/libdgr_ref.so and run on the GPU box (tests/test_vs_reference_cuda.py),
+//       oracle/_ref/libdgr_ref.so and run on the GPU box (tests/test_parity_gpu.py:
+//       test_oracle_matches_reference_cuda and the *_matches_reference_cuda tests),
 //   (2) against closed-form known-answer cases and fp64 finite differences
 //       (tests/test_oracle_kat.py), and against the reference's independent PyTorch
 //       helpers eval_sh / build_scaling_rotation re-stated in the tests.

@@ -76,7 +76,7 @@ def test_forward_matches_reference_cuda_bit_exact(fwd_variant):
         _lib.set_option("render_fwd_variant", 3)
 
 
-@pytest.mark.parametrize("bwd_variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("bwd_variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
 def test_backward_matches_reference_cuda(bwd_variant):
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
@@ -439,14 +439,16 @@ def test_speculative_second_half_equals_exact_path():
         RZ.SPECULATIVE = True
 
 
-@pytest.mark.parametrize("variant", [0, 1])
-def test_binning_variants_match_reference_lists(variant):
+@pytest.mark.parametrize("variant,depth_variant", [(0, 0), (1, 1), (1, 0), (0, 1)])
+def test_binning_variants_match_reference_lists(variant, depth_variant):
     """Both binning implementations -- 0: emit kernel + CUB radix sort + tile_ranges (binning.cu), 1: difference-array
-    ranges + two own radix passes with the emission fused in (tile_binning.cu, default) -- must give the reference's
-    point_list / ranges / R bit for bit, incl. a partial last tile row/column and a frame with > 256 tile columns."""
+    ranges + two own radix passes with the emission fused in (tile_binning.cu, default) -- and both depth orders -- 0: CUB
+    radix sort + CUB scan, 1: depth_sort.cu (default) -- must give the reference's point_list / ranges / R bit for bit,
+    incl. a partial last tile row/column and a frame with > 256 tile columns."""
     if not ref_cuda.available():
         pytest.skip("oracle/_ref not built")
     _lib.set_option("binning_variant", variant)
+    _lib.set_option("depth_sort_variant", depth_variant)
     try:
         cloud, _ = synth.make_config("c3", P=80_000)
         for (W, H, k) in [(333, 201, 5), (4160, 48, 1), (1600, 1200, 2)]:
@@ -460,6 +462,26 @@ def test_binning_variants_match_reference_lists(variant):
             assert torch.equal(ours["color"], ref["color"]), (W, H)
     finally:
         _lib.set_option("binning_variant", 1)
+        _lib.set_option("depth_sort_variant", 1)
+
+
+def test_depth_order_and_offsets_equal_cub_at_full_size():
+    """depth_sort.cu against the CUB sort + scan it replaces, at BASELINE config 3 size (1M keys, 39 % of them the
+    culled key 0xFFFFFFFF, ties between equal depths): depth_order and the instance total must be identical."""
+    from gaussianeditor_b200.rasterizer import forward_state_views
+    cloud, cams = synth.make_config("c3")
+    res = {}
+    try:
+        for v in (0, 1):
+            _lib.set_option("depth_sort_variant", v)
+            out = run_ours(cloud, cams[2], (0, 0, 0))
+            res[v] = (out["views"]["depth_order"].clone(), out["R"], out["views"]["point_list"].clone())
+    finally:
+        _lib.set_option("depth_sort_variant", 1)
+    vis = int((out["radii"] > 0).sum())
+    assert torch.equal(res[0][0][:vis], res[1][0][:vis])       # among the culled (equal keys) both are index-ordered too:
+    assert torch.equal(res[0][0], res[1][0])
+    assert res[0][1] == res[1][1] and torch.equal(res[0][2], res[1][2])
 
 
 def test_edit_loop_harness_runs_and_densifies():

@@ -71,5 +71,60 @@ for b in bufs:   # the ranks run one after the other on the shared arrays (no cl
     S.shard_render(b, frame[:3], frame[3:])
     acc = S.shard_backward_render(b, torch.from_numpy(dL).to(dev))
     S.shard_backward_preprocess(b, acc[b.plan.base:b.plan.base + b.plan.slice_len].contiguous())
+
+# round 2: both binning implementations x both depth orders, a speculative overflow (second half redone), the alpha
+# image with gradient, the camera gradients
+import gaussianeditor_b200.rasterizer as RZ
+for bvar, dvar in ((0, 0), (1, 1), (1, 0)):
+    _lib.set_option("binning_variant", bvar)
+    _lib.set_option("depth_sort_variant", dvar)
+    run_ours(cloud, cam, (0.1, 0.2, 0.3), dL=dL)
+    RZ._r_hint[(0, 3001, cam.image_width, cam.image_height)] = 10      # hopeless guess: overflow path
+    run_ours(cloud, cam, (0.1, 0.2, 0.3), dL=dL)
+_lib.set_option("binning_variant", 1)
+_lib.set_option("depth_sort_variant", 0)
+view = rs.viewmatrix.clone().requires_grad_(True)
+rs_cam = rs._replace(viewmatrix=view, projmatrix=rs.projmatrix.clone().requires_grad_(True),
+                     campos=rs.campos.clone().requires_grad_(True))
+ctg = cloud_tensors(cloud, dev, requires_grad=True)
+out = GaussianRasterizer(rs_cam, return_alpha=True, camera_grad=True)(
+    means3D=ctg["means3D"], means2D=torch.zeros_like(ctg["means3D"]), opacities=ctg["opacities"], shs=ctg["shs"],
+    scales=ctg["scales"], rotations=ctg["rotations"])
+((out[0] * torch.from_numpy(dL).to(dev)).sum() + out[3].sum()).backward()
+
+# sparse exchange, three virtual ranks on this GPU (tight capacity)
+from gaussianeditor_b200 import sparse_sharded as SS
+splans = [S.ShardPlan(3001, 3, r) for r in range(3)]
+ranks = [SS.SparseRank(p, dev, cam.image_width, cam.image_height) for p in splans]
+SS.link_virtual(ranks)
+
+
+def sparse_forward(cap):
+    for rk in ranks:
+        rk.matrix.zero_()
+    steps = []
+    for rk in ranks:
+        sl = lambda x: S.shard_slice(x, rk.plan)
+        steps.append(SS.sparse_preprocess(rk, rs, sl(ct["means3D"]), sl(ct["shs"]), empty, sl(ct["opacities"]),
+                                          sl(ct["scales"]), sl(ct["rotations"]), empty, cap))
+    m = torch.stack([rk.matrix for rk in ranks]).sum(0)
+    for rk in ranks:
+        rk.matrix.copy_(m)
+    return steps, [SS.sparse_order(st) for st in steps]
+
+
+steps, res = sparse_forward(ranks[0].cap_alloc)
+steps, res = sparse_forward(max(res[0][1], 1))
+for rk in ranks:
+    rk.frame.zero_()
+for st in steps:
+    SS.sparse_render(st, st.rk.frame[:3], st.rk.frame[3:])
+for rk in ranks:
+    SS.frame_broadcast(rk)
+accs = [SS.sparse_backward_render(st, torch.from_numpy(dL).to(dev)) for st in steps]
+for st, a in zip(steps, accs):
+    SS.sparse_return(st, a)
+for st in steps:
+    SS.sparse_backward_preprocess(st)
 torch.cuda.synchronize()
 print("SANITIZE_CASE_DONE")
