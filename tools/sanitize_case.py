@@ -86,11 +86,19 @@ _lib.set_option("depth_sort_variant", 0)
 view = rs.viewmatrix.clone().requires_grad_(True)
 rs_cam = rs._replace(viewmatrix=view, projmatrix=rs.projmatrix.clone().requires_grad_(True),
                      campos=rs.campos.clone().requires_grad_(True))
-ctg = cloud_tensors(cloud, dev, requires_grad=True)
-out = GaussianRasterizer(rs_cam, return_alpha=True, camera_grad=True)(
-    means3D=ctg["means3D"], means2D=torch.zeros_like(ctg["means3D"]), opacities=ctg["opacities"], shs=ctg["shs"],
-    scales=ctg["scales"], rotations=ctg["rotations"])
-((out[0] * torch.from_numpy(dL).to(dev)).sum() + out[3].sum()).backward()
+# camera gradients + alpha output. initcheck does not track TMA bulk stores (cp.async.bulk shared->global) as writes, so a
+# cudaMemcpy of the dL/dSH tensor they fill (autograd's copy into .grad) is reported as "uninitialized" byte for byte
+# (18006 reports = 576192 B / 32 in profiles/r02_sanitizer.txt). The TMA variant therefore runs with SH detached
+# (kernel identical, autograd drops the tensor without a copy) and the plain-store variant runs with SH attached.
+for pv, sh_grad in ((1, False), (0, True)):
+    _lib.set_option("preprocess_variant", pv)
+    ctg = cloud_tensors(cloud, dev, requires_grad=True)
+    shs = ctg["shs"] if sh_grad else ctg["shs"].detach()
+    out = GaussianRasterizer(rs_cam, return_alpha=True, camera_grad=True)(
+        means3D=ctg["means3D"], means2D=torch.zeros_like(ctg["means3D"]), opacities=ctg["opacities"], shs=shs,
+        scales=ctg["scales"], rotations=ctg["rotations"])
+    ((out[0] * torch.from_numpy(dL).to(dev)).sum() + out[3].sum()).backward()
+_lib.set_option("preprocess_variant", 1)
 
 # sparse exchange, three virtual ranks on this GPU (tight capacity)
 from gaussianeditor_b200 import sparse_sharded as SS
