@@ -459,14 +459,17 @@ def sharded_config4(dist, dev, rank, world, steps, warmup, points=None):
     if rast.mode == "sparse":
         from gaussianeditor_b200 import sparse_sharded as SS
         acc = {}
-        nph = 8
+        nph = 9
         for i in range(nph):
+            dist.barrier()                       # align the ranks: a late starter would show up as barrier wait
+            torch.cuda.synchronize()
             SS.TRACE = []
             sharded_step(i)
             torch.cuda.synchronize()
             tr = SS.TRACE
             for (n0, e0), (n1, e1) in zip(tr[:-1], tr[1:]):
-                acc[n1] = acc.get(n1, 0.0) + e0.elapsed_time(e1) / nph
+                acc.setdefault(n1, []).append(e0.elapsed_time(e1))
+        acc = {n: sorted(v)[len(v) // 2] for n, v in acc.items()}   # median over the traced steps
         SS.TRACE = None
         ph_names = list(acc.keys())
         t = torch.tensor([acc[n] for n in ph_names], device=dev)
