@@ -17,9 +17,10 @@
 //   (fixed rank order: deterministic)                           segment of source s into ret_s[d*cap ...]
 //   fused preprocess backward of the shard
 //
-// Counts n[s->d] travel in one [G,G] int matrix (all-reduced by the host binding: it doubles as the cross-rank
-// barrier after the push); a segment that overflows `cap` is detected from that matrix on every rank alike and the
-// step is redone with a larger capacity.
+// Counts n[s->d] travel in one [G,G] int matrix: every rank writes its row into every peer's copy inside the
+// cross-rank barrier that follows the push (gsr_peer_barrier, flag words in peer memory; virtual ranks and the gloo
+// tests sum the rows on the host instead); a segment that overflows `cap` is detected from that matrix on every rank
+// alike and the step is redone with a larger capacity.
 //
 // Everything except the peer transport is testable with VIRTUAL ranks on one GPU: peer pointers are then just other
 // buffers of the same device (tests/test_sharded.py).
@@ -391,7 +392,8 @@ struct PeerCtrl {
   uint32_t pad[7];
   int32_t matrix[GSR_MAX_PEERS][GSR_MAX_PEERS];
 };
-static_assert(sizeof(PeerCtrl) <= GSR_PEER_CTRL_BYTES && offsetof(PeerCtrl, matrix) == GSR_PEER_CTRL_MATRIX_OFFSET, "ctrl layout");
+static_assert(sizeof(PeerCtrl) <= GSR_PEER_CTRL_BYTES && offsetof(PeerCtrl, matrix) == GSR_PEER_CTRL_MATRIX_OFFSET &&
+                  offsetof(PeerCtrl, error) == GSR_PEER_CTRL_ERROR_OFFSET, "ctrl layout");
 
 struct BarrierArgs {
   PeerCtrl* ctrl[GSR_MAX_PEERS];

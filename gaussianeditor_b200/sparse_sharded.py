@@ -35,7 +35,7 @@ from .rasterizer import GaussianRasterizationSettings, _f32c, _make_cloud, _make
 from .sharded import ACC_STRIDE, Exchange, PeerWorkspace, ShardPlan, shard_slice
 
 MAXP = 8  # GSR_MAX_PEERS
-CTRL_BYTES, CTRL_MATRIX_OFFSET = 512, 64   # GSR_PEER_CTRL_BYTES, GSR_PEER_CTRL_MATRIX_OFFSET
+CTRL_BYTES, CTRL_MATRIX_OFFSET, CTRL_ERROR_OFFSET = 512, 64, 32   # GSR_PEER_CTRL_{BYTES,MATRIX_OFFSET,ERROR_OFFSET}
 
 
 def _align(n: int, a: int = 256) -> int:
@@ -64,6 +64,7 @@ class SparseRank:
             self.local = torch.empty(self.local_bytes, dtype=torch.uint8, device=device)
             self.radii_local = torch.zeros(max(plan.slice_len, 1), dtype=torch.int32, device=device)
             self.pinned = torch.zeros(2, dtype=torch.int32).pin_memory()
+            self.pinned_err = torch.zeros(1, dtype=torch.int32).pin_memory()
             self.peer = None
             if exchange is not None:   # real ranks: CUDA-IPC mapped block, created collectively
                 self.peer = PeerWorkspace(self.total_bytes, exchange, device)
@@ -75,6 +76,7 @@ class SparseRank:
                 self.base_ptrs[plan.rank] = self.block.data_ptr()
             self.block[:CTRL_BYTES].zero_()
             self.matrix = self.block[CTRL_MATRIX_OFFSET:CTRL_MATRIX_OFFSET + 4 * MAXP * MAXP].view(torch.int32).view(MAXP, MAXP)[:plan.world]
+            self.err_word = self.block[CTRL_ERROR_OFFSET:CTRL_ERROR_OFFSET + 4].view(torch.int32)
         self.epoch = 0
         if exchange is not None:
             torch.cuda.synchronize(device)
@@ -104,9 +106,21 @@ class SparseRank:
             t = self.scratch[name] = torch.empty(int(numel * grow) + 256, dtype=dtype, device=self.device)
         return t[:numel]
 
+    def queue_barrier_check(self):
+        """Async copy of the control block's sticky error word (set by a peer barrier that timed out) to pinned memory, on
+        the current stream; read it with ``raise_if_barrier_failed`` after the next point where the host has waited for
+        later work of that stream (the forward does: the instance count arrives behind it)."""
+        with torch.cuda.device(self.device):
+            self.pinned_err.copy_(self.err_word, non_blocking=True)
+
+    def raise_if_barrier_failed(self):
+        if int(self.pinned_err[0]) != 0:
+            raise RuntimeError(f"rank {self.plan.rank}: a peer barrier of the sparse exchange timed out (a peer rank died, "
+                               "hung or runs a different step sequence); the exchanged data of this step are not valid")
+
     def close(self):
         self.scratch.clear()
-        self.matrix = None
+        self.matrix = self.err_word = None
         if self.peer is not None:
             self.block = None
             self.peer.close()
@@ -343,8 +357,10 @@ class _SparseShardedRasterize(torch.autograd.Function):
             st = sparse_preprocess(rk, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, pool.cap)
             _mark("preprocess+push")
             peer_barrier(rk, with_row=True)                # counts + barrier: every push has landed
+            rk.queue_barrier_check()                       # sticky error word (this and earlier barriers) -> pinned
             _mark("count all-reduce")
-            R, max_count = sparse_order(st)
+            R, max_count = sparse_order(st)                # waits for R, queued behind that copy
+            rk.raise_if_barrier_failed()
             _mark("order")
             if max_count <= st.cap:
                 break

@@ -365,8 +365,10 @@ GSR_API int gsr_sparse_backward_preprocess(const gsr_settings* s, const gsr_clou
  * barrier on this block, identically on every rank. with_matrix_row != 0 first copies this rank's row into every
  * peer's matrix, so that after the barrier every rank holds the complete matrix. Work queued on `stream` behind this
  * call starts only after every rank has reached the same barrier (a rank that never arrives costs ~2 s and sets the
- * block's error word instead of hanging the GPU). */
+ * int32 error word at byte GSR_PEER_CTRL_ERROR_OFFSET of the OWN block to 1 instead of hanging the GPU; the word is
+ * sticky -- the host binding copies it out once per step and raises, gaussianeditor_b200/sparse_sharded.py). */
 #define GSR_PEER_CTRL_BYTES 512
+#define GSR_PEER_CTRL_ERROR_OFFSET 32
 #define GSR_PEER_CTRL_MATRIX_OFFSET 64
 GSR_API int gsr_peer_barrier(int32_t world, int32_t rank, void* const* peer_ctrl /* [world] host */, uint32_t epoch,
                      int32_t with_matrix_row, void* stream);

@@ -284,3 +284,33 @@ def test_workspace_pool_hands_out_distinct_workspaces_in_a_fixed_order():
     assert pool.take(dev) is wa and pool.take(dev) is wb and len(pool.all) == 2
     pool.close()
     assert pool.all == [] and pool.free == []
+
+
+@pytest.mark.gpu
+def test_peer_barrier_completes_and_reports_a_missing_rank():
+    """gsr_peer_barrier over (virtually) peer-mapped control blocks: two ranks that both arrive pass and leave the error
+    word clear; a rank whose peer never arrives gives up after its timeout and the host binding raises instead of using
+    the step's data (SparseRank.queue_barrier_check / raise_if_barrier_failed)."""
+    from gaussianeditor_b200 import sparse_sharded as SS
+    dev = torch.device("cuda")
+    plans = [S.ShardPlan(64, 2, r) for r in range(2)]
+    ranks = [SS.SparseRank(p, dev, 64, 48) for p in plans]
+    SS.link_virtual(ranks)
+    ranks[0].matrix[0, :2] = torch.tensor([3, 4], dtype=torch.int32, device=dev)
+    ranks[1].matrix[1, :2] = torch.tensor([5, 6], dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):            # the two barrier kernels must be able to run concurrently
+        SS.peer_barrier(ranks[1], with_row=True)
+    SS.peer_barrier(ranks[0], with_row=True)
+    for rk in ranks:
+        rk.queue_barrier_check()
+    torch.cuda.synchronize()
+    for rk in ranks:
+        rk.raise_if_barrier_failed()
+        assert rk.matrix[:2, :2].cpu().tolist() == [[3, 4], [5, 6]]     # both rows everywhere: the counts all-gather
+    SS.peer_barrier(ranks[0])                # rank 1 never arrives at barrier 2
+    ranks[0].queue_barrier_check()
+    torch.cuda.synchronize()
+    with pytest.raises(RuntimeError, match="peer barrier"):
+        ranks[0].raise_if_barrier_failed()
