@@ -314,3 +314,27 @@ def test_peer_barrier_completes_and_reports_a_missing_rank():
     torch.cuda.synchronize()
     with pytest.raises(RuntimeError, match="peer barrier"):
         ranks[0].raise_if_barrier_failed()
+
+
+def test_sparse_capacity_policy_is_deterministic_bounded_and_converges():
+    """Host logic of the sparse exchange's adaptive segment capacity (CPU): every rank derives the next capacity from
+    the same global count matrix, so the rule must be a pure function; it must cover the segment it was derived from
+    (no redo loop on a static scene), stay within the allocation, and keep the headroom small (every spare slot is a
+    hole the depth sort still carries)."""
+    from gaussianeditor_b200 import sparse_sharded as SS
+    alloc = 625_000
+    for mc in (0, 1, 4095, 4096, 138_897, 486_775, 600_000, 625_000, 10_000_000):
+        cap = SS.next_capacity(mc, alloc)
+        assert cap == SS.next_capacity(mc, alloc) and 1 <= cap <= alloc
+        assert cap % 4096 == 0 or cap == alloc
+        if mc * 1.10 + 4096 <= alloc:
+            assert cap >= mc and cap - mc <= 0.10 * mc + 2 * 4096
+        else:
+            assert cap >= min(mc, alloc)
+    # a scene whose largest segment grows by <10 % per frame never overflows once adapted
+    mc = 100_000
+    cap = SS.next_capacity(mc, alloc)
+    for _ in range(10):
+        mc = int(mc * 1.09)
+        assert mc <= cap
+        cap = SS.next_capacity(mc, alloc)
