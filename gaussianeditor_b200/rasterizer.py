@@ -15,6 +15,7 @@ Differences a caller can observe (all documented in DESIGN.md):
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import time
 from typing import NamedTuple
 
@@ -77,9 +78,11 @@ def _geometry_bytes(lib, P):
 
 
 def _pinned_i32(device):
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    """One pinned count word per (device, stream, host thread): two threads driving forwards on the same stream (e.g. the
+    autograd engine thread re-running a checkpointed forward) must not poll each other's word."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
     if key not in _pinned:
-        _pinned[key] = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _bounded_put(_pinned, key, torch.zeros(1, dtype=torch.int32).pin_memory(), limit=256)
     return _pinned[key]
 
 

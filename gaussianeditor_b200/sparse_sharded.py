@@ -353,19 +353,24 @@ class _SparseShardedRasterize(torch.autograd.Function):
         rk = pool.take()
         device = means3D.device
         _mark("start")
-        while True:
-            st = sparse_preprocess(rk, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, pool.cap)
-            _mark("preprocess+push")
-            peer_barrier(rk, with_row=True)                # counts + barrier: every push has landed
-            rk.queue_barrier_check()                       # sticky error word (this and earlier barriers) -> pinned
-            _mark("count all-reduce")
-            R, max_count = sparse_order(st)                # waits for R, queued behind that copy
-            rk.raise_if_barrier_failed()
-            _mark("order")
-            if max_count <= st.cap:
-                break
-            pool.redo += 1                                  # same decision on every rank (the matrix is global)
-            pool.cap = next_capacity(max_count, rk.cap_alloc)
+        try:
+            while True:
+                st = sparse_preprocess(rk, rs, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                       pool.cap)
+                _mark("preprocess+push")
+                peer_barrier(rk, with_row=True)                # counts + barrier: every push has landed
+                rk.queue_barrier_check()                       # sticky error word (this and earlier barriers) -> pinned
+                _mark("count all-reduce")
+                R, max_count = sparse_order(st)                # waits for R, queued behind that copy
+                rk.raise_if_barrier_failed()
+                _mark("order")
+                if max_count <= st.cap:
+                    break
+                pool.redo += 1                                  # same decision on every rank (the matrix is global)
+                pool.cap = next_capacity(max_count, rk.cap_alloc)
+        except BaseException:
+            pool.give(rk)                                       # a failed forward must not leak its workspace
+            raise
         pool.cap = next_capacity(max_count, rk.cap_alloc)
         weakref.finalize(st, pool.give, rk)
         # Every pixel has exactly one writer (the owner of its tile row; empty tiles are written too), so the frame needs

@@ -95,6 +95,9 @@ typedef struct gsr_grads {
 
 GSR_API int gsr_abi_version(void);
 GSR_API const char* gsr_last_error(void); /* thread-local, valid until the next failing call on this thread */
+/* Threading: every entry point only touches the buffers it is handed and enqueues on the stream it is handed, so calls
+ * from several host threads are safe as long as they do not share a workspace. The library-global pieces are the option
+ * table (gsr_set_option: set before the threads start), the launch counter (atomic) and the stage profile (mutex). */
 
 /* ---- workspace sizing (the three opaque buffers of rasterize_points.cu:62-69) ------------------------ */
 GSR_API size_t gsr_geometry_bytes(int32_t P);
