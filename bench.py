@@ -4,9 +4,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3]
 
-One "step" = one pass of the hot path over one camera: GaussianRasterizer.forward (preprocess -> depth order
--> scan -> R read-back -> instance emission -> tile sort -> ranges -> blend, plus output/workspace allocation)
-+ autograd backward of loss = (color * G).sum() with a fixed seeded G ~ U(0,1)[3,H,W]  (BASELINE.md timing
+One "step" = one pass of the hot path over one camera: GaussianRasterizer.forward (preprocess + tile-count
+difference array -> R to the host -> depth order -> scan -> ranges -> two radix passes over tile ids (the first
+generates the instances) -> blend, plus output/workspace allocation) + autograd backward of loss = (color * G).sum() with a fixed seeded G ~ U(0,1)[3,H,W]  (BASELINE.md timing
 protocol).  The 8 ring cameras of the config are cycled step by step.
 
   value  : W*H*steps / t / 1e6 with every input resident in HBM before the timed region (CUDA events, max over
@@ -23,9 +23,19 @@ protocol).  The 8 ring cameras of the config are cycled step by step.
   --impl reference : the reference's OWN CUDA path (oracle/_ref/libdgr_ref.so = its unmodified .cu files
            compiled for sm_100a) on the same workload; if that library is absent, the CPU oracle port.
 
-Extra objects on the JSON line: "roofline" (dominant kernel, CUDA-event timed inside this script),
-"cpu_baseline" (CPU oracle on the host cores, rank 0, N=1 only), "stages" (per-stage ms), "workload"
-descriptors (V, R, R/V, R/Ntile, mean n_contrib).
+  timing : every number is the MEDIAN of 5 back-to-back regions of K steps (each bracketed by barrier + synchronize);
+           the five region times are reported under "timing".
+  N > 1 also runs BASELINE config 4 (5M Gaussians, 1920x1080) through the Gaussian-sharded rasterizer over all N
+           GPUs (strong scaling) and reports it under "sharded_c4": ms/step, Mpixels/s, ratio to the plain rasterizer
+           on one GPU measured in the same run, bit-comparison of the 8 frames, per-phase times, exchange bytes.
+           (--no-sharded skips it; a watchdog prints the headline line anyway if a rank fails inside that leg.)
+
+Extra objects on the JSON line: "roofline" (dominant kernel, CUDA-event timed inside this script; "issue" = the
+instruction-issue lens for the FP32-bound render kernels), "cpu_baseline" (CPU oracle on the host cores, rank 0, N=1
+only), "stages_ms" (per-stage ms), "workload" descriptors (V, R, R/V, R/Ntile, mean n_contrib), "robustness" (the same
+step on a non-saturating variant of config 3 and on config 2, and the miss rate of the speculative second half over
+config 5's 48 cameras; --no-robustness skips it), "clocks", "gpu_launches". --option name=value sets a library
+option (kernel variants) for A/B runs.
 """
 from __future__ import annotations
 
