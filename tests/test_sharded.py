@@ -1,6 +1,7 @@
 """Gaussian-sharded multi-GPU path (gaussianeditor_b200/sharded.py, BASELINE config 4).
 
-CPU (not gpu): shard plan arithmetic and the three collectives under gloo, world_size 2.
+CPU (not gpu): shard plan arithmetic, the three collectives of the dense scheme under gloo (world_size 2), and the
+protocol of the sparse exchange restated in numpy and run over gloo (world_size 2 and 3).
 GPU: (a) the ownership logic of the kernels with VIRTUAL ranks on one device -- per-rank images must tile the
 single-GPU image bit-exactly and the summed accumulators must reproduce its gradients; (b) the real thing, one
 process per GPU over NCCL (needs >= 2 GPUs, skipped otherwise).
@@ -83,6 +84,110 @@ def test_gloo_world2_exchange_collectives():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_gloo_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    assert [out[r] for r in range(world)] == [True] * world
+
+
+# ---- sparse exchange: the protocol of csrc/sparse_exchange.cu restated in numpy and run over gloo ---------------------
+# What the CUDA kernels do per rank (sparse_mask / sparse_scan / sparse_push / sparse_order / sparse_return /
+# sparse_gather), with the peer stores replaced by gloo collectives: the claims under test are protocol claims --
+# (1) concatenating the per-source segments in rank order keeps GLOBAL index order, so a stable sort of the candidates
+#     by the 32-bit depth key alone equals the single-process (depth key, index) order of the Gaussians a rank blends;
+# (2) holes (unused segment slots) sort behind every candidate; (3) the count matrix tells every rank alike whether
+# a segment overflowed; (4) the return path brings every partial row back to its owner and adding them in ascending
+# rank order is deterministic and complete.
+CULLED_KEY = np.uint32(0xFFFFFFFF)
+
+
+def _model_cloud(P, gy, seed=11):
+    """Synthetic per-Gaussian facts the exchange depends on: visibility, tile-row span [ymin, ymax), depth key (with ties)."""
+    rng = np.random.default_rng(seed)
+    visible = rng.random(P) < 0.6
+    ymin = rng.integers(0, gy, P)
+    span = np.where(rng.random(P) < 0.05, rng.integers(1, gy + 1, P), rng.integers(1, 4, P))   # a few huge splats
+    ymax = np.minimum(gy, ymin + span)
+    key = rng.integers(0, 50, P).astype(np.uint32)            # few distinct depths: ties must fall back to the index
+    return visible, ymin, ymax, key
+
+
+def _dest_mask(visible, ymin, ymax, world):
+    m = np.zeros(visible.shape[0], dtype=np.uint32)
+    for i in np.nonzero(visible)[0]:
+        if ymax[i] - ymin[i] >= world:
+            m[i] = (1 << world) - 1
+        else:
+            for y in range(ymin[i], ymax[i]):
+                m[i] |= 1 << (y % world)
+    return m
+
+
+def _sparse_model_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, gy = 1003, 9
+        plan = S.ShardPlan(P, world, rank)
+        visible, ymin, ymax, key = _model_cloud(P, gy)
+        sl = slice(plan.base, plan.base + plan.count)
+        mask = _dest_mask(visible[sl], ymin[sl], ymax[sl], world)          # owner side: sparse_mask
+        ids = np.arange(plan.base, plan.base + plan.count)
+        ok = True
+        for cap in (plan.slice_len, None, 3):     # worst case, tight (set below from the matrix), overflowing
+            # sparse_scan: slot of Gaussian i in the list for destination d = number of earlier own Gaussians with bit d
+            slots = {d: np.cumsum((mask >> d) & 1) - ((mask >> d) & 1) for d in range(world)}
+            row = torch.tensor([int(((mask >> d) & 1).sum()) for d in range(world)], dtype=torch.int64)
+            rows = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(rows, row)                                       # the count matrix (peer_barrier with_row)
+            matrix = torch.stack(rows).numpy()                               # matrix[s, d] = n[s -> d]
+            if cap is None:
+                cap = int(matrix.max())
+            overflow = int(matrix.max()) > cap
+            # sparse_push: segment [src] of every destination's candidate arrays; unused slots = holes with the culled key
+            seg_id = np.full((world, cap), -1, dtype=np.int64)
+            seg_key = np.full((world, cap), CULLED_KEY, dtype=np.uint32)
+            for d in range(world):
+                sel = np.nonzero((mask >> d) & 1)[0]
+                sel = sel[slots[d][sel] < cap]
+                seg_id[d, slots[d][sel]] = ids[sel]
+                seg_key[d, slots[d][sel]] = key[sl][sel]
+            got_id = [torch.zeros(world, cap, dtype=torch.int64) for _ in range(world)]
+            got_key = [torch.zeros(world, cap, dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(got_id, torch.from_numpy(seg_id))
+            dist.all_gather(got_key, torch.from_numpy(seg_key.astype(np.int64)))
+            cand_id = np.concatenate([got_id[s][rank].numpy() for s in range(world)])      # segments in rank order
+            cand_key = np.concatenate([got_key[s][rank].numpy() for s in range(world)]).astype(np.uint32)
+            ok &= overflow == (cap == 3)
+            if overflow:
+                continue                                                     # every rank sees it in the same matrix
+            # sparse_order: stable sort by the 32-bit key alone
+            order = np.argsort(cand_key, kind="stable")
+            n_real = int(matrix[:, rank].sum())
+            ok &= bool((cand_id[order[n_real:]] == -1).all())                # holes sort last
+            full_mask = _dest_mask(visible, ymin, ymax, world)
+            mine = np.nonzero((full_mask >> rank) & 1)[0]                    # what a single process would blend here
+            want = mine[np.lexsort((mine, key[mine]))]                       # (depth key, global index)
+            ok &= bool(np.array_equal(cand_id[order[:n_real]], want))
+            # backward: a partial row per candidate, returned to slot (dst=rank, slot) of the owner, gathered in rank order
+            part = np.where(cand_id >= 0, np.float32(0.1) * cand_id.astype(np.float32) + np.float32(rank + 1), 0).astype(np.float32)
+            back = [torch.zeros(world * cap, dtype=torch.float32) for _ in range(world)]
+            dist.all_gather(back, torch.from_numpy(part))                    # back[d][s*cap + slot]
+            total = np.zeros(plan.count, dtype=np.float32)
+            expect = np.zeros(plan.count, dtype=np.float32)
+            for d in range(world):                                           # ascending rank: deterministic
+                sel = np.nonzero((mask >> d) & 1)[0]
+                total[sel] += back[d].numpy()[rank * cap + slots[d][sel]]
+                expect[sel] += np.float32(0.1) * ids[sel].astype(np.float32) + np.float32(d + 1)
+            ok &= bool(np.array_equal(total, expect)) and bool((total[mask == 0] == 0).all())
+        out[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_sparse_exchange_protocol_keeps_global_order(world):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sparse_model_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     assert [out[r] for r in range(world)] == [True] * world
 
 
