@@ -181,3 +181,32 @@ def test_product_package_never_touches_the_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b|oracle/_ref|cpu_oracle|liboracle|libdgr_ref", text, re.M):
                         bad.append(os.path.join(dp, f))
     assert bad == []
+
+
+@pytest.mark.parametrize("stride,phase", [(1, 0), (2, 1), (3, 0), (8, 5)])
+def test_tile_count_difference_array_identities(stride, phase):
+    """The arithmetic behind csrc/tile_binning.cu, restated in numpy: every visible Gaussian adds +1/-1/-1/+1 at the four
+    corners of its tile rectangle; (a) the 2-D prefix sum of that array is the per-tile instance count, and (b) the total
+    over the tiles of the owned rows (ty % stride == phase) is the plain weighted sum
+    sum_entries diff[y][x] * (gx - x) * #owned rows >= y  -- which is how R reaches the host without any prefix pass."""
+    rng = np.random.default_rng(stride * 10 + phase)
+    gx, gy, n = 13, 11, 400
+    x0 = rng.integers(0, gx, n); y0 = rng.integers(0, gy, n)
+    x1 = np.minimum(gx, x0 + rng.integers(0, 5, n)); y1 = np.minimum(gy, y0 + rng.integers(0, 6, n))   # some empty rects
+    diff = np.zeros((gy + 1, gx + 1), dtype=np.int64)
+    brute = np.zeros((gy, gx), dtype=np.int64)
+    for a, b, c, d in zip(x0, y0, x1, y1):
+        if c > a and d > b:
+            diff[b, a] += 1; diff[b, c] -= 1; diff[d, a] -= 1; diff[d, c] += 1
+            brute[b:d, a:c] += 1
+    counts = diff.cumsum(0).cumsum(1)[:gy, :gx]
+    assert np.array_equal(counts, brute)
+    owned = np.array([(ty % stride) == phase for ty in range(gy)])
+    rows_from = np.array([owned[y:].sum() for y in range(gy + 1)])            # owned rows with ty >= y
+    weights = rows_from[:, None] * (gx - np.arange(gx + 1))[None, :]
+    assert int((diff * weights).sum()) == int(brute[owned].sum())
+    # ranges: exclusive scan of the owned tiles' counts in row-major order, (0, 0) for empty tiles (the reference's memset)
+    flat = np.where(owned[:, None], brute, 0).reshape(-1)
+    excl = np.concatenate([[0], flat.cumsum()[:-1]])
+    ranges = [(int(e), int(e + c)) if c else (0, 0) for e, c in zip(excl, flat)]
+    assert ranges[-1][1] in (0, int(flat.sum())) and all(b - a == c for (a, b), c in zip(ranges, flat))
