@@ -10,10 +10,12 @@
 // from its very end.  Here:
 //   * the walk starts at tile_last = max n_contrib of the tile (written by the forward): on a saturated scene
 //     three quarters of every list lie behind the last contributor of all 256 pixels and are never loaded;
-//   * warp variants (1/2/3 branchy, 4..9 branch-light; DEFAULT 4 = one warp per half tile, 0.572 ms at config 3): a
+//   * warp variants (1/2/3 branchy, 4..9 branch-light, 10/11 skip by sub-block mask, 12..14 register caps; DEFAULT 14 =
+//     one warp per half tile, 96 registers -> 5 CTAs/SM, updates of sub-blocks without a hit skipped warp-uniformly:
+//     0.544 ms at config 3; the A/B of all of them is in DESIGN.md section 3): a
 //     warp owns a whole tile, half or a quarter of it, each lane owns one pixel of each of its
 //     8x4 sub-blocks; the nine partial sums are first accumulated over the lane's own pixels in registers,
-//     then summed across the warp with a transposing butterfly (14 shuffles for 9 values instead of 45), and
+//     then summed across the warp with a transposing butterfly (16 shuffles for 9 values instead of 45), and
 //     only then added to global memory: 9 atomics per (tile, splat) instead of 9 per (pixel, splat);
 //   * the same opacity-aware sub-block culling as the forward (render_fwd.cu) removes splats whose
 //     alpha>=1/255 ellipse misses the sub-block before any pixel looks at them.
