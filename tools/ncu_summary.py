@@ -23,7 +23,7 @@ COLS = {
 }
 STAGES = {"render_bwd": "render_bwd", "render_fwd": "render_fwd", "preprocess_bwd": "preprocess_bwd",
           "preprocess_fwd": "preprocess_fwd", "emit_instances": "emit_instances", "tile_ranges": "tile_prefix",
-          "tile_sort_pass1": "tile_sort_pass_kernel<(bool)1", "tile_sort_pass2": "tile_sort_pass_kernel<(bool)0",
+          "tile_sort_pass1": "tile_sort_pass_kernel<1", "tile_sort_pass2": "tile_sort_pass_kernel<0",
           "tile_count": "tile_count"}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 
